@@ -1,0 +1,222 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on seeded inputs.
+
+TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the
+fixtures it writes are committed so the GPU box (no reference tree) can still pin the
+oracle and the CUDA path against real reference outputs.
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+Seeds follow the reference's own seed (commander_explore.py:400 -> 3787).
+"""
+import copy
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refshim  # noqa: E402
+
+REF = refshim.install()
+
+import models  # noqa: E402  (reference)
+from models.layers import MlpBlock_Real, GraphNorm, normalize, Matmul, ColumnMaxPooling  # noqa: E402
+from loaders import data_generator as dg  # noqa: E402
+from maskedtensors import maskedtensor as mt  # noqa: E402
+from toolbox.losses import triplet_loss  # noqa: E402
+from toolbox.metrics import accuracy_max  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+SEED = 3787
+
+
+def seed_all(s):
+    random.seed(s)
+    np.random.seed(s)
+    torch.manual_seed(s)
+
+
+def perturb_(model, gen):
+    """Move conv biases and GraphNorm affine off their trivial init (0 / 1 / 0) so the
+    fixtures exercise every term; the reference model then computes with these values."""
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("convs.0.bias") or name.endswith("convs.1.bias") or name.endswith("convs.2.bias"):
+                p.copy_((torch.rand(p.shape, generator=gen) - 0.5) * 0.2)
+            elif name.endswith("gn.weight"):
+                w = 1.0 + (torch.rand(p.shape, generator=gen) - 0.5)
+                sign = torch.where(torch.rand(p.shape, generator=gen) < 0.2, -1.0, 1.0)
+                p.copy_(w * sign)
+            elif name.endswith("gn.bias"):
+                p.copy_((torch.rand(p.shape, generator=gen) - 0.5) * 0.5)
+
+
+def build_model(c, num_blocks, depth, cst=True):
+    cfg = yaml.safe_load(open(os.path.join(REF, "default_config.yaml")))
+    arch = copy.deepcopy(cfg["arch"])
+    arch["node_emb"].update(num_blocks=num_blocks, in_features=c, out_features=c, depth_of_mlp=depth)
+    if not cst:
+        arch["node_emb"]["constant_n_vertices"] = False
+    return models.get_siamese_model_exp(arch, cfg["train"])
+
+
+def gen_pairs(generative, n, p, noise, count):
+    W1, W2 = [], []
+    for _ in range(count):
+        g, W = dg.GENERATOR_FUNCTIONS[generative](p, n)
+        Wn = dg.noise_erdos_renyi(g, W, noise, p)
+        W1.append(W)
+        W2.append(Wn)
+    return W1, W2
+
+
+def sd_np(model):
+    return {"sd/" + k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def dense_case(name, generative, n, p, noise, pairs, c, num_blocks, depth, with_grads=True, with_taps=True):
+    seed_all(SEED)
+    model = build_model(c, num_blocks, depth)
+    perturb_(model, torch.Generator().manual_seed(SEED + 1))
+    W1, W2 = gen_pairs(generative, n, p, noise, pairs)
+    x1 = torch.stack([dg.adjacency_matrix_to_tensor_representation(w) for w in W1])
+    x2 = torch.stack([dg.adjacency_matrix_to_tensor_representation(w) for w in W2])
+    model.train()
+    out1 = model.node_embedder({"input": x1})
+    out2 = model.node_embedder({"input": x2})
+    e1, e2 = out1["ne/suffix"], out2["ne/suffix"]
+    scores = model({"input": x1}, {"input": x2})
+    loss_mean = triplet_loss("mean")(scores)
+    loss_mom = triplet_loss("mean_of_mean")(scores)
+    correct, total = accuracy_max(scores)
+    arrs = dict(sd_np(model))
+    arrs.update(
+        W1=torch.stack(W1).numpy().astype(np.uint8), W2=torch.stack(W2).numpy().astype(np.uint8),
+        x1_first=x1[0].numpy(), emb1=e1.detach().numpy(), emb2=e2.detach().numpy(),
+        scores=scores.detach().numpy(), loss_mean=np.float64(loss_mean.item()),
+        loss_mean_of_mean=np.float64(loss_mom.item()), acc=np.array([correct, total], dtype=np.int64),
+        meta=np.array([n, c, num_blocks, depth, pairs], dtype=np.int64))
+    if with_taps:
+        # every Network node output for graph 0 of side 1 (models/utils.py:63-69 returns all of them)
+        for k, v in out1.items():
+            if k.endswith(("mlp1", "mlp2", "mult", "mlp3")):
+                t = v[0].detach()
+                arrs["tap/" + k] = t[:4].numpy().astype(np.float32)          # first 4 channels, full planes
+                arrs["tapstat/" + k] = torch.stack((t.mean(dim=(1, 2)), t.std(dim=(1, 2)),
+                                                     t.amax(dim=(1, 2)))).numpy()
+    if with_grads:
+        model.zero_grad()
+        loss_mean.backward()
+        for k, p_ in model.named_parameters():
+            arrs["grad/" + k] = p_.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(name, "loss", float(loss_mean), "acc", correct, total, "emb absmax", float(e1.abs().max()))
+
+
+def ragged_case(name, sizes, p, noise, c, num_blocks, depth):
+    seed_all(SEED)
+    model_cst = build_model(c, num_blocks, depth, cst=True)
+    perturb_(model_cst, torch.Generator().manual_seed(SEED + 2))
+    model_msk = build_model(c, num_blocks, depth, cst=False)
+    model_msk.load_state_dict(model_cst.state_dict())
+    g1, g2, W1, W2 = [], [], [], []
+    for n in sizes:
+        g, W = dg.GENERATOR_FUNCTIONS["ErdosRenyi"](p, n)
+        Wn = dg.noise_erdos_renyi(g, W, noise, p)
+        W1.append(W), W2.append(Wn)
+        g1.append(dg.adjacency_matrix_to_tensor_representation(W))
+        g2.append(dg.adjacency_matrix_to_tensor_representation(Wn))
+    # (1) per-graph dense loop (the reference's own ragged oracle idiom, test_maskedtensor.py:22-34)
+    per1 = [model_cst.node_embedder({"input": g.unsqueeze(0)})["ne/suffix"][0] for g in g1]
+    per2 = [model_cst.node_embedder({"input": g.unsqueeze(0)})["ne/suffix"][0] for g in g2]
+    # (2) the reference's masked embedder on from_list batches (both sides named 'N': SURVEY 8a defect (i))
+    m1 = mt.from_list(g1, dims=(1, 2), base_name="N")
+    m2 = mt.from_list(g2, dims=(1, 2), base_name="N")
+    me1 = model_msk.node_embedder({"input": m1})["ne/suffix"]
+    me2 = model_msk.node_embedder({"input": m2})["ne/suffix"]
+    nmax = max(sizes)
+    per_scores = [torch.matmul(a.t(), b) for a, b in zip(per1, per2)]
+    msc = mt.from_list(per_scores, dims=(0, 1))     # as test_maskedtensor.py:221-244 feeds the head
+    loss_mean = triplet_loss("mean")(msc)
+    loss_mom = triplet_loss("mean_of_mean")(msc)
+    correct, total = accuracy_max(msc)
+    arrs = dict(sd_np(model_cst))
+    arrs.update(sizes=np.array(sizes, dtype=np.int64), meta=np.array([nmax, c, num_blocks, depth, len(sizes)]),
+                masked_emb1=me1.tensor.rename(None).detach().numpy(),
+                masked_emb2=me2.tensor.rename(None).detach().numpy(),
+                masked_input1=m1.tensor.rename(None).numpy(), mask_N=m1.mask_dict["N"].rename(None).numpy(),
+                loss_mean=np.float64(loss_mean.item()), loss_mean_of_mean=np.float64(loss_mom.item()),
+                acc=np.array([correct, total], dtype=np.int64))
+    for i, n in enumerate(sizes):
+        arrs[f"W1/{i}"] = W1[i].numpy().astype(np.uint8)
+        arrs[f"W2/{i}"] = W2[i].numpy().astype(np.uint8)
+        arrs[f"emb1/{i}"] = per1[i].detach().numpy()
+        arrs[f"emb2/{i}"] = per2[i].detach().numpy()
+        arrs[f"scores/{i}"] = per_scores[i].detach().numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    d = max(float((me1.tensor.rename(None)[i, :, :n] - per1[i]).abs().max()) for i, n in enumerate(sizes))
+    print(name, "loss", float(loss_mean), "masked-vs-pergraph maxabs", d)
+
+
+def layers_case(name):
+    """The reference's own layer-level test shapes (test_maskedtensor.py:36-47,167-188), seeded."""
+    seed_all(SEED)
+    nfeat, sizes = 16, [12, 9, 15]
+    lst = [torch.empty((nfeat, n, n)).normal_() for n in sizes]
+    mlp = MlpBlock_Real(nfeat, 32, 2)
+    gn = GraphNorm(nfeat)
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(SEED + 3)
+        for m in (mlp.gn, gn):
+            m.weight.copy_(1.0 + (torch.rand(m.weight.shape, generator=gen) - 0.5))
+            m.bias.copy_((torch.rand(m.bias.shape, generator=gen) - 0.5) * 0.5)
+        for cv in mlp.convs:
+            cv.bias.copy_((torch.rand(cv.bias.shape, generator=gen) - 0.5) * 0.2)
+    arrs = {"sizes": np.array(sizes)}
+    for k, v in mlp.state_dict().items():
+        arrs["mlp/" + k] = v.numpy().copy()
+    for k, v in gn.state_dict().items():
+        arrs["gn/" + k] = v.numpy().copy()
+    other = [torch.empty((nfeat, n, n)).normal_() for n in sizes]
+    for i, t in enumerate(lst):
+        b = t.unsqueeze(0)
+        arrs[f"x/{i}"] = t.numpy()
+        arrs[f"x2/{i}"] = other[i].numpy()
+        arrs[f"mlp_out/{i}"] = mlp(b)[0].detach().numpy()
+        arrs[f"gn_out/{i}"] = gn(b)[0].detach().numpy()
+        arrs[f"normalize_out/{i}"] = normalize(b)[0].numpy()
+        arrs[f"matmul_out/{i}"] = Matmul()(b, other[i].unsqueeze(0))[0].numpy()
+        arrs[f"colmax_out/{i}"] = ColumnMaxPooling()(b)[0].numpy()
+    # masked versions through the reference MaskedTensor (constant_n_vertices=False twins)
+    mlp_m = MlpBlock_Real(nfeat, 32, 2, constant_n_vertices=False)
+    mlp_m.load_state_dict(mlp.state_dict())
+    m = mt.from_list(lst, dims=(1, 2))
+    arrs["masked_mlp_out"] = mlp_m(m).tensor.rename(None).detach().numpy()
+    arrs["masked_normalize_out"] = normalize(m, constant_n_vertices=False).tensor.rename(None).numpy()
+    sc = [torch.empty((n, n)).normal_() for n in sizes]
+    for i, s in enumerate(sc):
+        arrs[f"score/{i}"] = s.numpy()
+    msc = mt.from_list(sc, dims=(0, 1))
+    arrs["loss_mean"] = np.float64(triplet_loss("mean")(msc).item())
+    arrs["loss_mean_of_mean"] = np.float64(triplet_loss("mean_of_mean")(msc).item())
+    arrs["acc"] = np.array(accuracy_max(msc), dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(name, "ok")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    # cfg1 (BASELINE.json configs[0]) at reduced pair count: default_config arch, ER n=50 p=0.2 noise 0.1
+    dense_case("cfg1_er50_c32", "ErdosRenyi", 50, 0.2, 0.1, pairs=4, c=32, num_blocks=4, depth=3)
+    # headline architecture (C=64, 4 blocks) on small regular graphs
+    dense_case("cfg3_reg40_c64", "Regular", 40, 0.2, 0.1, pairs=2, c=64, num_blocks=4, depth=3,
+               with_grads=False, with_taps=False)
+    # tiny model for fast CPU checks incl. gradients
+    dense_case("tiny_er12_c8", "ErdosRenyi", 12, 0.4, 0.1, pairs=3, c=8, num_blocks=2, depth=2)
+    ragged_case("ragged_c16", [9, 14, 11, 6, 20], 0.4, 0.1, c=16, num_blocks=2, depth=2)
+    layers_case("layers_f16")
