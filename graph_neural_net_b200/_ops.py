@@ -1,0 +1,277 @@
+"""torch.autograd glue over the C ABI: one Function per reference operator.
+
+Each forward/backward is a single call into libfgnn_b200.so on the caller's current CUDA
+stream.  Inputs must be CUDA float32 tensors; anything else raises (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _npg(n_dev: Optional[torch.Tensor]):
+    return L.ptr(n_dev) if n_dev is not None else None
+
+
+def make_mlp_params(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                    gn_w: Optional[torch.Tensor], gn_b: Optional[torch.Tensor], eps: float,
+                    keep: list) -> L.MlpParams:
+    """Fill an fgnn_mlp_params from Conv2d/GraphNorm tensors.  `keep` receives every temporary
+    that must outlive the C call (contiguous copies)."""
+    p = L.MlpParams()
+    depth = len(weights)
+    if depth > L.FGNN_MAX_DEPTH:
+        raise L.FgnnError(f"depth_of_mlp {depth} > {L.FGNN_MAX_DEPTH}")
+    w0 = weights[0]
+    p.c_in = int(w0.shape[1])
+    p.c_out = int(w0.shape[0])
+    p.depth = depth
+    for k in range(depth):
+        w = L.require_cuda_f32(weights[k].detach().reshape(weights[k].shape[0], -1), f"convs[{k}].weight")
+        b = biases[k]
+        if b is None:
+            b = torch.zeros(w.shape[0], device=w.device, dtype=torch.float32)
+        b = L.require_cuda_f32(b.detach(), f"convs[{k}].bias")
+        keep += [w, b]
+        p.w[k] = w.data_ptr()
+        p.b[k] = b.data_ptr()
+    if gn_w is not None:
+        gw = L.require_cuda_f32(gn_w.detach().reshape(-1), "gn.weight")
+        gb = L.require_cuda_f32(gn_b.detach().reshape(-1), "gn.bias")
+        keep += [gw, gb]
+        p.gn_w = gw.data_ptr()
+        p.gn_b = gb.data_ptr()
+    else:
+        p.gn_w = None
+        p.gn_b = None
+    p.eps = float(eps)
+    return p
+
+
+class MlpFunction(torch.autograd.Function):
+    """MlpBlock_Real forward/backward (reference models/layers.py:109-131)."""
+
+    @staticmethod
+    def forward(ctx, x, n_dev, eps, depth, gn_w, gn_b, *wb):
+        lib = L.get_lib()
+        x = L.require_cuda_f32(x, "x")
+        weights, biases = wb[:depth], wb[depth:]
+        keep = []
+        p = make_mlp_params(weights, biases, gn_w, gn_b, eps, keep)
+        G, Ci, N, N2 = x.shape
+        if N != N2 or Ci != p.c_in:
+            raise L.FgnnError(f"MlpBlock_Real: bad input shape {tuple(x.shape)} for c_in={p.c_in}")
+        y = torch.empty((G, p.c_out, N, N), device=x.device, dtype=torch.float32)
+        stats = torch.empty((G, p.c_out, 2), device=x.device, dtype=torch.float32)
+        nbytes = lib.fgnn_mlp_workspace_bytes(G, p.c_in, p.c_out, p.depth, N)
+        ws = L.workspace(x.device, nbytes)
+        L.check(lib.fgnn_mlp_fwd_f32(C.byref(p), L.ptr(x), L.ptr(y), L.ptr(stats), G, N, _npg(n_dev),
+                                     L.ptr(ws), ws.numel(), L.stream_ptr(x.device)), "fgnn_mlp_fwd_f32")
+        ctx.save_for_backward(x, stats, n_dev if n_dev is not None else torch.empty(0), gn_w, gn_b, *wb)
+        ctx.has_n = n_dev is not None
+        ctx.eps, ctx.depth = eps, depth
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.get_lib()
+        x, stats, n_dev, gn_w, gn_b, *wb = ctx.saved_tensors
+        n_dev = n_dev if ctx.has_n else None
+        depth = ctx.depth
+        weights, biases = wb[:depth], wb[depth:]
+        keep = []
+        p = make_mlp_params(weights, biases, gn_w, gn_b, ctx.eps, keep)
+        g = L.MlpGrads()
+        dws = [torch.zeros_like(w, dtype=torch.float32).reshape(w.shape[0], -1).contiguous() for w in weights]
+        dbs = [torch.zeros(w.shape[0], device=x.device, dtype=torch.float32) for w in weights]
+        dgw = torch.zeros(p.c_out, device=x.device, dtype=torch.float32)
+        dgb = torch.zeros(p.c_out, device=x.device, dtype=torch.float32)
+        for k in range(depth):
+            g.w[k] = dws[k].data_ptr()
+            g.b[k] = dbs[k].data_ptr()
+        g.gn_w, g.gn_b = dgw.data_ptr(), dgb.data_ptr()
+        G, Ci, N, _ = x.shape
+        dy = L.require_cuda_f32(dy, "dy")
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        nbytes = lib.fgnn_mlp_workspace_bytes(G, p.c_in, p.c_out, p.depth, N)
+        ws = L.workspace(x.device, nbytes)
+        L.check(lib.fgnn_mlp_bwd_f32(C.byref(p), C.byref(g), L.ptr(x), L.ptr(stats), L.ptr(dy), L.ptr(dx),
+                                     G, N, _npg(n_dev), L.ptr(ws), ws.numel(), L.stream_ptr(x.device)),
+                "fgnn_mlp_bwd_f32")
+        grads_w = [dws[k].reshape(weights[k].shape) for k in range(depth)]
+        grads_b = [dbs[k] if biases[k] is not None else None for k in range(depth)]
+        return (dx, None, None, None,
+                dgw.reshape(gn_w.shape) if gn_w is not None else None,
+                dgb.reshape(gn_b.shape) if gn_b is not None else None, *grads_w, *grads_b)
+
+
+class MatmulFunction(torch.autograd.Function):
+    """Matmul.forward = torch.matmul over the last two dims (reference models/layers.py:161-162)."""
+
+    @staticmethod
+    def forward(ctx, a, b, n_dev):
+        lib = L.get_lib()
+        a = L.require_cuda_f32(a, "xs1")
+        b = L.require_cuda_f32(b, "xs2")
+        if a.shape != b.shape or a.dim() != 4 or a.shape[-1] != a.shape[-2]:
+            raise L.FgnnError(f"Matmul: expected two (B,C,N,N) tensors, got {tuple(a.shape)} {tuple(b.shape)}")
+        G, Cc, N, _ = a.shape
+        out = torch.empty_like(a)
+        L.check(lib.fgnn_matmul_fwd_f32(L.ptr(a), L.ptr(b), L.ptr(out), G, Cc, N, _npg(n_dev),
+                                        L.stream_ptr(a.device)), "fgnn_matmul_fwd_f32")
+        ctx.save_for_backward(a, b, n_dev if n_dev is not None else torch.empty(0))
+        ctx.has_n = n_dev is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.get_lib()
+        a, b, n_dev = ctx.saved_tensors
+        n_dev = n_dev if ctx.has_n else None
+        dout = L.require_cuda_f32(dout, "dout")
+        G, Cc, N, _ = a.shape
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        L.check(lib.fgnn_matmul_bwd_f32(L.ptr(a), L.ptr(b), L.ptr(dout), L.ptr(da), L.ptr(db), G, Cc, N,
+                                        _npg(n_dev), L.stream_ptr(a.device)), "fgnn_matmul_bwd_f32")
+        return da, db, None
+
+
+class ColMaxFunction(torch.autograd.Function):
+    """ColumnMaxPooling.forward = torch.max(x, -1)[0] (reference models/layers.py:194-203)."""
+
+    @staticmethod
+    def forward(ctx, x, n_dev):
+        lib = L.get_lib()
+        x = L.require_cuda_f32(x, "x")
+        G, Cc, N, M = x.shape
+        if N != M:
+            raise L.FgnnError("ColumnMaxPooling: expected (B,C,N,N)")
+        out = torch.empty((G, Cc, N), device=x.device, dtype=torch.float32)
+        arg = torch.empty((G, Cc, N), device=x.device, dtype=torch.int32)
+        L.check(lib.fgnn_colmax_fwd_f32(L.ptr(x), L.ptr(out), L.ptr(arg), G, Cc, N, _npg(n_dev),
+                                        L.stream_ptr(x.device)), "fgnn_colmax_fwd_f32")
+        ctx.save_for_backward(arg, n_dev if n_dev is not None else torch.empty(0))
+        ctx.has_n = n_dev is not None
+        ctx.shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.get_lib()
+        arg, n_dev = ctx.saved_tensors
+        n_dev = n_dev if ctx.has_n else None
+        dout = L.require_cuda_f32(dout, "dout")
+        G, Cc, N, _ = ctx.shape
+        dx = torch.empty(ctx.shape, device=dout.device, dtype=torch.float32)
+        L.check(lib.fgnn_colmax_bwd_f32(L.ptr(dout), L.ptr(arg), L.ptr(dx), G, Cc, N, _npg(n_dev),
+                                        L.stream_ptr(dout.device)), "fgnn_colmax_bwd_f32")
+        return dx, None
+
+
+class ScoresFunction(torch.autograd.Function):
+    """scores[b] = e1[b]^T e2[b] (reference models/trainers.py:67)."""
+
+    @staticmethod
+    def forward(ctx, e1, e2, n_dev):
+        lib = L.get_lib()
+        e1 = L.require_cuda_f32(e1, "e1")
+        e2 = L.require_cuda_f32(e2, "e2")
+        if e1.shape != e2.shape or e1.dim() != 3:
+            raise L.FgnnError(f"siamese head: expected two (B,C,N) tensors, got {tuple(e1.shape)} {tuple(e2.shape)}")
+        G, Cc, N = e1.shape
+        s = torch.empty((G, N, N), device=e1.device, dtype=torch.float32)
+        L.check(lib.fgnn_scores_fwd_f32(L.ptr(e1), L.ptr(e2), L.ptr(s), G, Cc, N, _npg(n_dev),
+                                        L.stream_ptr(e1.device)), "fgnn_scores_fwd_f32")
+        ctx.save_for_backward(e1, e2, n_dev if n_dev is not None else torch.empty(0))
+        ctx.has_n = n_dev is not None
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        lib = L.get_lib()
+        e1, e2, n_dev = ctx.saved_tensors
+        n_dev = n_dev if ctx.has_n else None
+        ds = L.require_cuda_f32(ds, "dscores")
+        G, Cc, N = e1.shape
+        de1, de2 = torch.empty_like(e1), torch.empty_like(e2)
+        L.check(lib.fgnn_scores_bwd_f32(L.ptr(e1), L.ptr(e2), L.ptr(ds), L.ptr(de1), L.ptr(de2), G, Cc, N,
+                                        _npg(n_dev), L.stream_ptr(e1.device)), "fgnn_scores_bwd_f32")
+        return de1, de2, None
+
+
+class CrossEntropyIdentityFunction(torch.autograd.Function):
+    """Per-graph sum_i CE(scores[i,:], i) (reference toolbox/losses.py:27-31), with the row argmax
+    count as a by-product (toolbox/metrics.py:125-134).  Returns (ce_sum[G], correct[G])."""
+
+    @staticmethod
+    def forward(ctx, scores, n_dev):
+        lib = L.get_lib()
+        scores = L.require_cuda_f32(scores, "raw_scores")
+        G, N, M = scores.shape
+        if N != M:
+            raise L.FgnnError("raw_scores must be (B,N,N)")
+        ce = torch.empty(G, device=scores.device, dtype=torch.float32)
+        correct = torch.empty(G, device=scores.device, dtype=torch.int32)
+        lse = torch.empty((G, N), device=scores.device, dtype=torch.float32)
+        L.check(lib.fgnn_ce_argmax_fwd_f32(L.ptr(scores), L.ptr(ce), L.ptr(correct), L.ptr(lse), G, N,
+                                           _npg(n_dev), L.stream_ptr(scores.device)), "fgnn_ce_argmax_fwd_f32")
+        ctx.save_for_backward(scores, lse, n_dev if n_dev is not None else torch.empty(0))
+        ctx.has_n = n_dev is not None
+        ctx.mark_non_differentiable(correct)
+        return ce, correct
+
+    @staticmethod
+    def backward(ctx, dce, _dcorrect):
+        lib = L.get_lib()
+        scores, lse, n_dev = ctx.saved_tensors
+        n_dev = n_dev if ctx.has_n else None
+        G, N, _ = scores.shape
+        coef = L.require_cuda_f32(dce, "dce")
+        ds = torch.empty_like(scores)
+        L.check(lib.fgnn_ce_bwd_f32(L.ptr(scores), L.ptr(lse), L.ptr(coef), L.ptr(ds), G, N, _npg(n_dev),
+                                    L.stream_ptr(scores.device)), "fgnn_ce_bwd_f32")
+        return ds, None
+
+
+def graphnorm_fwd(x: torch.Tensor, n_dev, gn_w, gn_b, eps: float) -> torch.Tensor:
+    """GraphNorm / normalize forward (reference models/layers.py:68-80); no autograd (use MlpBlock_Real
+    for training -- the standalone norm is not on the training path)."""
+    lib = L.get_lib()
+    x = L.require_cuda_f32(x, "b")
+    G, Cc, N, M = x.shape
+    if N != M:
+        raise L.FgnnError("GraphNorm expects (B,C,N,N)")
+    y = torch.empty_like(x)
+    stats = torch.empty((G, Cc, 2), device=x.device, dtype=torch.float32)
+    gw = L.require_cuda_f32(gn_w.detach().reshape(-1), "weight") if gn_w is not None else None
+    gb = L.require_cuda_f32(gn_b.detach().reshape(-1), "bias") if gn_b is not None else None
+    L.check(lib.fgnn_graphnorm_fwd_f32(L.ptr(x), L.ptr(y), L.ptr(stats), L.ptr(gw), L.ptr(gb), float(eps),
+                                       G, Cc, N, _npg(n_dev), L.stream_ptr(x.device)), "fgnn_graphnorm_fwd_f32")
+    return y
+
+
+def embed_fwd(params: L.EmbedParams, precision: int, x: torch.Tensor, c_out: int,
+              n_dev: Optional[torch.Tensor], n_host: Optional[List[int]]) -> torch.Tensor:
+    """Fused node_embedding forward: x (G,c_in,N,N) -> (G,C,N)."""
+    lib = L.get_lib()
+    x = L.require_cuda_f32(x, "input")
+    G, _, N, M = x.shape
+    if N != M:
+        raise L.FgnnError("input must be (B,F,N,N)")
+    emb = torch.empty((G, c_out, N), device=x.device, dtype=torch.float32)
+    nbytes = lib.fgnn_embed_workspace_bytes(C.byref(params), precision, G, N)
+    if nbytes == 0:
+        raise L.FgnnError("fgnn_embed_workspace_bytes returned 0: " + lib.fgnn_last_error().decode())
+    ws = L.workspace(x.device, nbytes)
+    nh = None
+    if n_host is not None:
+        nh = (C.c_int32 * G)(*n_host)
+    L.check(lib.fgnn_embed_fwd(C.byref(params), precision, L.ptr(x), L.ptr(emb), G, N, _npg(n_dev),
+                               C.cast(nh, C.c_void_p) if nh is not None else None, L.ptr(ws), ws.numel(),
+                               L.stream_ptr(x.device)), "fgnn_embed_fwd")
+    return emb

@@ -1,0 +1,18 @@
+// Internal interface of the tensor-core (tcgen05 / TMEM / TMA) path (fgnn_tc.cu).
+#pragma once
+#include "fgnn_common.cuh"
+
+namespace fgnn {
+namespace tc {
+
+size_t embed_workspace_bytes(const fgnn_embed_params& p, int G, int N);
+int embed_fwd(const fgnn_embed_params& p, int precision, const float* x, float* emb, int G, int N,
+              const int32_t* n_per_graph, const int32_t* n_per_graph_host, void* ws, size_t ws_bytes,
+              cudaStream_t st);
+
+size_t debug_matmul_workspace_bytes(int G, int C, int N);
+int debug_matmul(int precision, const float* a, const float* b, float* out, int G, int C, int N,
+                 const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace fgnn

@@ -1,0 +1,173 @@
+/* fgnn_b200.h -- C ABI of libfgnn_b200.so: the B200 (sm_100a) implementation of the
+ * 2-FGNN siamese hot path of mlelarge/graph_neural_net.
+ *
+ * The reference has no FFI: its boundary is the Python API.  Each entry point
+ * below states which reference call site it replaces (paths relative to the reference tree).
+ * The Python mirror of the reference interface (graph_neural_net_b200/models, maskedtensors,
+ * toolbox) binds these symbols with ctypes; see INTEGRATION.md for the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense row-major fp32 with the reference's shapes: activations (G,C,N,N),
+ *     node vectors (G,C,N), scores (G,N,N); N is the padded size (Nmax of the batch);
+ *   - n_per_graph: int32[G] true vertex counts (prefix masks of maskedtensor.from_list,
+ *     maskedtensors/maskedtensor.py:40-46), or NULL when every graph has exactly N vertices;
+ *     padded positions of every output are written as exact zeros (maskedtensor.py:87-90);
+ *   - stream: a cudaStream_t passed as void*; all work is enqueued there, no hidden syncs;
+ *   - the library never allocates device memory: callers size scratch with the *_workspace_bytes
+ *     query and own every buffer;
+ *   - return value: FGNN_OK or an fgnn_status error code; fgnn_last_error() gives text.
+ */
+#ifndef FGNN_B200_H
+#define FGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  FGNN_OK = 0,
+  FGNN_ERR_INVALID = 1,      /* bad argument (shape, null pointer, alignment)            */
+  FGNN_ERR_UNSUPPORTED = 2,  /* valid request this build cannot serve (e.g. C > 128)     */
+  FGNN_ERR_CUDA = 3,         /* a CUDA runtime / driver call failed                      */
+  FGNN_ERR_WORKSPACE = 4     /* workspace too small                                      */
+} fgnn_status;
+
+typedef enum {
+  FGNN_FP32 = 0,  /* CUDA-core fp32 everywhere: parity mode (<= 1e-4 rel. on embeddings)        */
+  FGNN_BF16 = 1,  /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate / statistics        */
+  FGNN_FP16 = 2   /* same kernels and speed with fp16 operands (8x smaller rounding error)     */
+} fgnn_precision;
+
+#define FGNN_MAX_DEPTH 8
+#define FGNN_MAX_BLOCKS 16
+
+/* One MlpBlock_Real: depth x Conv2d(k=1) + GraphNorm  (models/layers.py:109-131).
+ * w[k]: (c_out, c_in_k) row-major (== Conv2d weight (Co,Ci,1,1)), b[k]: (c_out).
+ * gn_w/gn_b: (c_out) (== GraphNorm (1,C,1,1), models/layers.py:47-69). */
+typedef struct {
+  int32_t c_in;
+  int32_t c_out;
+  int32_t depth;
+  const float* w[FGNN_MAX_DEPTH];
+  const float* b[FGNN_MAX_DEPTH];
+  const float* gn_w;
+  const float* gn_b;
+  float eps; /* 1e-5 in the reference */
+} fgnn_mlp_params;
+
+/* Gradients of the above, same shapes; accumulated into (+=), caller zeroes them. */
+typedef struct {
+  float* w[FGNN_MAX_DEPTH];
+  float* b[FGNN_MAX_DEPTH];
+  float* gn_w;
+  float* gn_b;
+} fgnn_mlp_grads;
+
+/* One `block` of models/blocks_emb.py:16-27: mlp3(cat[mlp1(x) @ mlp2(x), x]). */
+typedef struct {
+  fgnn_mlp_params mlp1, mlp2, mlp3;
+} fgnn_block_params;
+
+/* node_embedding: num_blocks blocks + ColumnMaxPooling (models/blocks_emb.py:29-43). */
+typedef struct {
+  int32_t num_blocks;
+  fgnn_block_params block[FGNN_MAX_BLOCKS];
+} fgnn_embed_params;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* fgnn_version(void);
+const char* fgnn_last_error(void); /* thread-local text of the last failure */
+/* 1 if the current device is sm_100 (tcgen05 paths usable), 0 otherwise */
+int fgnn_device_supports_tcgen05(void);
+
+/* ---- fp32 per-operator entry points (each mirrors one reference module) ------------------ */
+
+/* MlpBlock_Real.forward (models/layers.py:126-131), also its MaskedTensor form
+ * (maskedtensor.py:230-238 conv2d override + layers.py:76-79 per-graph n).
+ * x (G,c_in,N,N) -> y (G,c_out,N,N).  stats (G,c_out,2) receives {mean, 1/(2*sqrt(n*(var+eps)))}
+ * of the pre-norm activations (kept for backward).  workspace: fgnn_mlp_workspace_bytes. */
+size_t fgnn_mlp_workspace_bytes(int32_t G, int32_t c_in, int32_t c_out, int32_t depth, int32_t N);
+int fgnn_mlp_fwd_f32(const fgnn_mlp_params* p, const float* x, float* y, float* stats, int32_t G,
+                     int32_t N, const int32_t* n_per_graph, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* Backward of the above.  Hidden activations are recomputed from x (nothing but x and stats is
+ * saved).  dy (G,c_out,N,N) -> dx (G,c_in,N,N) (may be NULL), parameter grads accumulated. */
+int fgnn_mlp_bwd_f32(const fgnn_mlp_params* p, const fgnn_mlp_grads* g, const float* x,
+                     const float* stats, const float* dy, float* dx, int32_t G, int32_t N,
+                     const int32_t* n_per_graph, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* GraphNorm.forward / normalize (models/layers.py:68-80).  gn_w/gn_b may be NULL (plain
+ * normalize).  stats as above (may be NULL). */
+int fgnn_graphnorm_fwd_f32(const float* x, float* y, float* stats, const float* gn_w,
+                           const float* gn_b, float eps, int32_t G, int32_t C, int32_t N,
+                           const int32_t* n_per_graph, void* stream);
+
+/* Matmul.forward: torch.matmul over the last two dims (models/layers.py:161-162).
+ * a,b,out (G,C,N,N); padded rows/cols ignored and written as zero. */
+int fgnn_matmul_fwd_f32(const float* a, const float* b, float* out, int32_t G, int32_t C, int32_t N,
+                        const int32_t* n_per_graph, void* stream);
+/* da = dout @ b^T, db = a^T @ dout (either may be NULL). */
+int fgnn_matmul_bwd_f32(const float* a, const float* b, const float* dout, float* da, float* db,
+                        int32_t G, int32_t C, int32_t N, const int32_t* n_per_graph, void* stream);
+
+/* ColumnMaxPooling.forward: max over the last dim (models/layers.py:194-203; masked form
+ * maskedtensor.py:213-228).  x (G,C,N,N) -> out (G,C,N); argmax (G,C,N) int32 may be NULL. */
+int fgnn_colmax_fwd_f32(const float* x, float* out, int32_t* argmax, int32_t G, int32_t C, int32_t N,
+                        const int32_t* n_per_graph, void* stream);
+int fgnn_colmax_bwd_f32(const float* dout, const int32_t* argmax, float* dx, int32_t G, int32_t C,
+                        int32_t N, const int32_t* n_per_graph, void* stream);
+
+/* Siamese head: scores[g] = e1[g]^T e2[g]  (models/trainers.py:67).  e1,e2 (G,C,N) -> (G,N,N). */
+int fgnn_scores_fwd_f32(const float* e1, const float* e2, float* scores, int32_t G, int32_t C,
+                        int32_t N, const int32_t* n_per_graph, void* stream);
+int fgnn_scores_bwd_f32(const float* e1, const float* e2, const float* dscores, float* de1,
+                        float* de2, int32_t G, int32_t C, int32_t N, const int32_t* n_per_graph,
+                        void* stream);
+
+/* Row-softmax cross-entropy against the identity matching + row argmax, one pass
+ * (toolbox/losses.py:20-34 and toolbox/metrics.py:118-141 without the per-graph host loop).
+ * scores (G,N,N) -> ce_sum[G] (sum_i lse_i - s_ii), correct[G] (#rows with argmax == i),
+ * row_lse (G,N) may be NULL (kept for backward). */
+int fgnn_ce_argmax_fwd_f32(const float* scores, float* ce_sum, int32_t* correct, float* row_lse,
+                           int32_t G, int32_t N, const int32_t* n_per_graph, void* stream);
+/* dscores[g,i,j] = coef[g] * (softmax(scores[g,i,:])[j] - [i==j]); coef folds the loss
+ * reduction and the upstream gradient. */
+int fgnn_ce_bwd_f32(const float* scores, const float* row_lse, const float* coef, float* dscores,
+                    int32_t G, int32_t N, const int32_t* n_per_graph, void* stream);
+
+/* ---- fused embedder (the hot path proper) ------------------------------------------------ */
+
+/* node_embedding forward for G graphs: x (G,c_in0,N,N) fp32 -> emb (G,C,N) fp32.
+ * Replaces Network.forward over the 4-block DAG + ColumnMaxPooling
+ * (models/utils.py:63-69, models/blocks_emb.py:16-43, models/trainers.py:64-65).
+ *   precision FGNN_FP32 : composition of the fp32 operators above.
+ *   precision FGNN_BF16 / FGNN_FP16 : TMA + tcgen05/TMEM kernels; activations live in HBM as
+ *     16-bit pre-normalisation planes, GraphNorm is folded into the consumers.
+ * workspace: fgnn_embed_workspace_bytes(...) bytes, 1024-byte aligned. */
+size_t fgnn_embed_workspace_bytes(const fgnn_embed_params* p, int32_t precision, int32_t G, int32_t N);
+int fgnn_embed_fwd(const fgnn_embed_params* p, int32_t precision, const float* x, float* emb,
+                   int32_t G, int32_t N, const int32_t* n_per_graph,
+                   const int32_t* n_per_graph_host, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Number of kernels the last call on this thread launched (bench.py's gpu_launches). */
+int64_t fgnn_launch_count(void);
+void fgnn_reset_launch_count(void);
+
+/* Diagnostics for the tensor-core building blocks (tests call these to check each kernel in
+ * isolation against the fp32 operators): 16-bit planes are (G*C) planes of pitch_rows x pitch_cols. */
+int fgnn_debug_tc_matmul(int32_t precision, const float* a, const float* b, float* out, int32_t G,
+                         int32_t C, int32_t N, const int32_t* n_per_graph, void* workspace,
+                         size_t workspace_bytes, void* stream);
+size_t fgnn_debug_tc_matmul_workspace_bytes(int32_t G, int32_t C, int32_t N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGNN_B200_H */

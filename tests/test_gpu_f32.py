@@ -1,0 +1,154 @@
+"""GPU parity tests of the fp32 CUDA operators (through the C ABI / Python mirror) against the
+oracle and the golden vectors produced by the reference.  Run with `pytest -m gpu` on the B200."""
+import numpy as np
+import pytest
+import torch
+
+import graph_neural_net_b200 as pkg
+from graph_neural_net_b200.maskedtensors import maskedtensor as mt
+from graph_neural_net_b200.models.layers import (MlpBlock_Real, GraphNorm, normalize, Matmul,
+                                                 ColumnMaxPooling, Concat)
+from graph_neural_net_b200.toolbox.losses import triplet_loss
+from graph_neural_net_b200.toolbox.metrics import accuracy_max, accuracy_linear_assignment
+from oracle import fgnn_oracle as O
+from tests.helpers import load_golden, state_dict_of, rel_fro
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_TOL = 1e-4          # north_star: fp32 mode within 1e-4 relative on node embeddings
+
+
+def feats(W):
+    return torch.stack([O.adjacency_to_features(torch.from_numpy(w.astype(np.float32))) for w in W])
+
+
+def build_model(z, precision="fp32"):
+    n, c, nb, depth, _ = [int(v) for v in z["meta"]]
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=nb,
+                    in_features=c, out_features=c, depth_of_mlp=depth)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(state_dict_of(z))
+    return model.to(DEV).set_precision(precision)
+
+
+def test_library_loaded_and_device():
+    lib = pkg.get_lib()
+    assert lib.fgnn_device_supports_tcgen05() == 1
+
+
+def test_layers_match_reference_fixture():
+    z = load_golden("layers_f16")
+    sizes = [int(s) for s in z["sizes"]]
+    mlp = MlpBlock_Real(16, 32, 2)
+    mlp.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("mlp/")})
+    gn = GraphNorm(16)
+    gn.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("gn/")})
+    mlp, gn = mlp.to(DEV), gn.to(DEV)
+    xs = [torch.from_numpy(z[f"x/{i}"]) for i in range(len(sizes))]
+    x2s = [torch.from_numpy(z[f"x2/{i}"]) for i in range(len(sizes))]
+    with torch.no_grad():
+        for i, n in enumerate(sizes):
+            x = xs[i][None].to(DEV)
+            assert rel_fro(mlp(x)[0].cpu(), z[f"mlp_out/{i}"]) < 2e-5
+            assert rel_fro(gn(x)[0].cpu(), z[f"gn_out/{i}"]) < 2e-5
+            assert rel_fro(normalize(x)[0].cpu(), z[f"normalize_out/{i}"]) < 2e-5
+            assert rel_fro(Matmul()(x, x2s[i][None].to(DEV))[0].cpu(), z[f"matmul_out/{i}"]) < 2e-5
+            assert torch.equal(ColumnMaxPooling()(x)[0].cpu(), torch.from_numpy(z[f"colmax_out/{i}"]))
+        # masked batch == per-graph results, exact zeros in the padding (reference test idiom)
+        m = mt.from_list(xs, dims=(1, 2)).to(DEV)
+        m2 = mt.from_list(x2s, dims=(1, 2)).to(DEV)
+        mlp_m = MlpBlock_Real(16, 32, 2, constant_n_vertices=False).to(DEV)
+        mlp_m.load_state_dict(mlp.state_dict())
+        out = mlp_m(m)
+        assert isinstance(out, mt.MaskedTensor) and out.tensor.names == ('B', None, 'N', 'N_')
+        assert rel_fro(out.tensor.rename(None).cpu(), z["masked_mlp_out"]) < 2e-5
+        nm = normalize(m, constant_n_vertices=False).tensor.rename(None).cpu()
+        assert rel_fro(nm, z["masked_normalize_out"]) < 2e-5
+        mm = Matmul()(m, m2).tensor.rename(None).cpu()
+        cm = ColumnMaxPooling()(m)
+        assert cm.tensor.names == ('B', None, 'N')
+        for i, n in enumerate(sizes):
+            assert float(out.tensor.rename(None)[i, :, n:, :].abs().max()) == 0
+            assert float(out.tensor.rename(None)[i, :, :, n:].abs().max()) == 0
+            assert rel_fro(mm[i, :, :n, :n], z[f"matmul_out/{i}"]) < 2e-5
+            assert float(mm[i, :, n:, :].abs().max()) == 0 and float(mm[i, :, :, n:].abs().max()) == 0
+            assert torch.equal(cm.tensor.rename(None)[i, :, :n].cpu(), torch.from_numpy(z[f"colmax_out/{i}"]))
+            assert float(cm.tensor.rename(None)[i, :, n:].abs().max()) == 0
+        sc = mt.from_list([torch.from_numpy(z[f"score/{i}"]) for i in range(len(sizes))], dims=(0, 1)).to(DEV)
+        assert abs(float(triplet_loss("mean")(sc)) - float(z["loss_mean"])) < 1e-5
+        assert abs(float(triplet_loss("mean_of_mean")(sc)) - float(z["loss_mean_of_mean"])) < 1e-5
+        assert list(accuracy_max(sc)) == list(z["acc"])
+
+
+@pytest.mark.parametrize("name", ["tiny_er12_c8", "cfg1_er50_c32", "cfg3_reg40_c64"])
+def test_fp32_model_matches_reference(name):
+    z = load_golden(name)
+    model = build_model(z)
+    x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    with torch.no_grad():
+        outs = model.node_embedder({"input": x1})
+        e1 = outs["ne/suffix"]
+        e2 = model.embed({"input": x2})
+        scores = model({"input": x1}, {"input": x2})
+        assert rel_fro(e1.cpu(), z["emb1"]) < FP32_TOL and rel_fro(e2.cpu(), z["emb2"]) < FP32_TOL
+        assert rel_fro(scores.cpu(), z["scores"]) < FP32_TOL
+        assert abs(float(triplet_loss("mean")(scores)) - float(z["loss_mean"])) < 1e-4
+        assert abs(float(triplet_loss("mean_of_mean")(scores)) - float(z["loss_mean_of_mean"])) < 1e-4
+        # per-stage parity: every intermediate node the reference's Network.forward returns
+        for k, v in z.items():
+            if k.startswith("tap/"):
+                assert rel_fro(outs[k[4:]][0, :4].cpu(), v) < FP32_TOL, k
+        # fused fp32 entry point == node-by-node execution
+        fused = model.node_embedder.forward_fused(x1, "fp32")
+        assert rel_fro(fused.cpu(), e1.cpu()) < 1e-6
+    # argmax / accuracy parity on the reference's own scores (bit-identical inputs => identical counts)
+    ref_scores = torch.from_numpy(z["scores"]).to(DEV)
+    assert list(accuracy_max(ref_scores)) == list(z["acc"])
+    lap = accuracy_linear_assignment(ref_scores)
+    assert lap[1] == int(z["acc"][1]) and 0 <= lap[0] <= lap[1]
+
+
+def test_ragged_batch_matches_per_graph_reference():
+    z = load_golden("ragged_c16")
+    sizes = [int(s) for s in z["sizes"]]
+    nmax, c, nb, depth, _ = [int(v) for v in z["meta"]]
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=nb,
+                    in_features=c, out_features=c, depth_of_mlp=depth, constant_n_vertices=False)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(state_dict_of(z))
+    model = model.to(DEV)
+    g1 = [O.adjacency_to_features(torch.from_numpy(z[f"W1/{i}"].astype(np.float32))) for i in range(len(sizes))]
+    g2 = [O.adjacency_to_features(torch.from_numpy(z[f"W2/{i}"].astype(np.float32))) for i in range(len(sizes))]
+    m1 = mt.from_list(g1, dims=(1, 2), base_name='N').to(DEV)
+    m2 = mt.from_list(g2, dims=(1, 2), base_name='N').to(DEV)
+    with torch.no_grad():
+        e1 = model.embed({"input": m1})
+        assert rel_fro(e1.tensor.rename(None).cpu(), z["masked_emb1"]) < FP32_TOL
+        scores = model({"input": m1}, {"input": m2})
+        assert isinstance(scores, mt.MaskedTensor)
+        for i, n in enumerate(sizes):
+            assert rel_fro(scores[i].cpu(), z[f"scores/{i}"]) < FP32_TOL
+            assert float(e1.tensor.rename(None)[i, :, n:].abs().max()) == 0
+        assert abs(float(triplet_loss("mean")(scores)) - float(z["loss_mean"])) < 1e-4
+        assert abs(float(triplet_loss("mean_of_mean")(scores)) - float(z["loss_mean_of_mean"])) < 1e-4
+        fused = model.node_embedder.forward_fused(m1, "fp32")
+        assert rel_fro(fused.tensor.rename(None).cpu(), z["masked_emb1"]) < FP32_TOL
+
+
+def test_head_backward_matches_autograd():
+    """loss -> scores -> embeddings gradients of the fused head vs torch autograd on the oracle."""
+    gen = torch.Generator().manual_seed(5)
+    e1 = torch.randn((3, 8, 21), generator=gen)
+    e2 = torch.randn((3, 8, 21), generator=gen)
+    a1, a2 = e1.clone().requires_grad_(True), e2.clone().requires_grad_(True)
+    O.triplet_loss(O.siamese_scores(a1, a2)).backward()
+    b1, b2 = e1.to(DEV).requires_grad_(True), e2.to(DEV).requires_grad_(True)
+    from graph_neural_net_b200 import _ops
+    loss = triplet_loss()(_ops.ScoresFunction.apply(b1, b2, None))
+    loss.backward()
+    assert rel_fro(b1.grad.cpu(), a1.grad) < 1e-5 and rel_fro(b2.grad.cpu(), a2.grad) < 1e-5
+
+
+def test_cpu_tensors_are_rejected():
+    with pytest.raises(pkg.FgnnError):
+        Matmul()(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
