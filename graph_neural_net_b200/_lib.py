@@ -73,6 +73,8 @@ _SIGNATURES = {
     "fgnn_embed_workspace_bytes": (_sz, [C.POINTER(EmbedParams), _i32, _i32, _i32]),
     "fgnn_embed_fwd": (C.c_int, [C.POINTER(EmbedParams), _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "fgnn_debug_tc_matmul_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "fgnn_debug_tc_mlp_workspace_bytes": (_sz, [_i32] * 5),
+    "fgnn_debug_tc_mlp": (C.c_int, [_i32, C.POINTER(MlpParams), _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fgnn_debug_tc_matmul": (C.c_int, [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
 }
 

@@ -224,4 +224,15 @@ int fgnn_debug_tc_matmul(int32_t precision, const float* a, const float* b, floa
                           (cudaStream_t)stream);
 }
 
+size_t fgnn_debug_tc_mlp_workspace_bytes(int32_t G, int32_t c_in, int32_t c_out, int32_t depth, int32_t N) {
+  return tc::debug_mlp_workspace_bytes(G, c_in, c_out, depth, N);
+}
+
+int fgnn_debug_tc_mlp(int32_t precision, const fgnn_mlp_params* p, const float* x, float* y, int32_t G,
+                      int32_t N, const int32_t* n_per_graph, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  FGNN_CHECK_ARG(p != nullptr, "null params");
+  return tc::debug_mlp(precision, *p, x, y, G, N, n_per_graph, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

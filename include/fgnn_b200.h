@@ -166,6 +166,12 @@ int fgnn_debug_tc_matmul(int32_t precision, const float* a, const float* b, floa
                          int32_t C, int32_t N, const int32_t* n_per_graph, void* workspace,
                          size_t workspace_bytes, void* stream);
 size_t fgnn_debug_tc_matmul_workspace_bytes(int32_t G, int32_t C, int32_t N);
+/* One MlpBlock_Real through the tensor-core conv-chain kernel (fold -> chain -> statistics ->
+ * normalise): x (G,c_in,N,N) fp32 -> y (G,c_out,N,N) fp32, comparable with fgnn_mlp_fwd_f32. */
+size_t fgnn_debug_tc_mlp_workspace_bytes(int32_t G, int32_t c_in, int32_t c_out, int32_t depth, int32_t N);
+int fgnn_debug_tc_mlp(int32_t precision, const fgnn_mlp_params* p, const float* x, float* y, int32_t G,
+                      int32_t N, const int32_t* n_per_graph, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }
