@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the 2-FGNN siamese forward (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            # this implementation
+    python bench.py --impl reference --steps 3 --warmup 1    # CPU reference arm (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[2] (the configuration the metric is quoted on): siamese 2-FGNN,
+embedding width 64, 4 blocks, depth-3 MLPs, regular graphs n=500 (d=100), ER noise 0.1, 64 pairs
+per GPU, bf16 forward.  One step = one siamese forward over the batch: both embedders, the
+E1^T E2 scores, and the fused row-softmax CE / argmax head.  Synthetic data, random-init weights.
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same
+through the public Python API from pinned host buffers (H2D of the step's inputs and D2H of the
+loss/accuracy inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (n, width, blocks, depth, pairs per GPU, regular degree or None (ER p=0.2))
+    "cfg3_regular_n500_c64_b64_fwd": dict(n=500, c=64, blocks=4, depth=3, pairs=64, regular=True),
+    "cfg2_er_n200_c32_b128_fwd": dict(n=200, c=32, blocks=4, depth=3, pairs=128, regular=False),
+    "cfg1_er_n50_c32_b32_fwd": dict(n=50, c=32, blocks=4, depth=3, pairs=32, regular=False),
+}
+DEFAULT_WORKLOAD = "cfg3_regular_n500_c64_b64_fwd"
+METRIC = "graph-pairs/sec 2-FGNN siamese fwd at n=500"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=p.get("bf16_tflops", 1590.0), sustained=p.get("bf16_tflops_sustained", 1400.0),
+                    hbm=p.get("hbm_gbs", 6650.0), src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+def make_inputs(cfg, pairs, seed):
+    from oracle import fgnn_oracle as O
+    gen = torch.Generator().manual_seed(seed)
+    n = cfg["n"]
+    deg = int(0.2 * n) if cfg["regular"] else None
+    x1 = torch.empty((pairs, 2, n, n), dtype=torch.float32)
+    x2 = torch.empty((pairs, 2, n, n), dtype=torch.float32)
+    for i in range(pairs):
+        a, b = O.synthetic_pair(n, 0.2, 0.1, gen, regular_degree=deg)
+        x1[i], x2[i] = a, b
+    return x1, x2
+
+
+def make_state_dict(cfg, seed=3787):
+    from oracle import fgnn_oracle as O
+    gen = torch.Generator().manual_seed(seed)
+    return O.xavier_state_dict(2, cfg["c"], cfg["blocks"], cfg["depth"], gen)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+def cpu_reference_rate(cfg, steps, warmup, pairs_per_step=1):
+    """The reference algorithm (oracle port, fp32 torch CPU, all host threads) on a bounded sample."""
+    from oracle import fgnn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_state_dict(cfg)
+    x1, x2 = make_inputs(cfg, pairs_per_step, seed=11)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            s = O.siamese_forward(x1, x2, sd)
+            float(O.triplet_loss(s))
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return pairs_per_step * len(times) / total, cores, total / len(times)
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    rate, cores, sec = cpu_reference_rate(cfg, args.steps, args.warmup)
+    sample = f"1 pair per step ({args.steps} timed steps, {args.warmup} warm-up) of the same workload, fp32 torch CPU"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "n": cfg["n"], "width": cfg["c"], "blocks": cfg["blocks"],
+                       "pairs_per_step": 1},
+            "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (profiling runs only)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch.distributed as dist
+    import graph_neural_net_b200 as pkg
+    from graph_neural_net_b200.toolbox.losses import triplet_loss
+    from graph_neural_net_b200 import _ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = pkg.get_lib()
+    peaks = load_peaks()
+
+    pairs = args.pairs if args.pairs > 0 else cfg["pairs"]
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=cfg["blocks"],
+                    in_features=cfg["c"], out_features=cfg["c"], depth_of_mlp=cfg["depth"])
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(make_state_dict(cfg))
+    model = model.to(dev).set_precision(args.precision)
+    loss_fn = triplet_loss()
+
+    x1_h, x2_h = make_inputs(cfg, pairs, seed=100 + rank)
+    x1_h, x2_h = x1_h.pin_memory(), x2_h.pin_memory()
+    x1_d, x2_d = x1_h.to(dev), x2_h.to(dev)
+    res_h = torch.empty(2, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        scores = model({"input": x1_d}, {"input": x2_d})
+        ce, correct = _ops.CrossEntropyIdentityFunction.apply(scores, None)
+        return ce, correct
+
+    def step_e2e():
+        x1_d.copy_(x1_h, non_blocking=True)
+        x2_d.copy_(x2_h, non_blocking=True)
+        scores = model({"input": x1_d}, {"input": x2_d})
+        ce, correct = _ops.CrossEntropyIdentityFunction.apply(scores, None)
+        res = torch.stack((ce.sum() / (pairs * cfg["n"]), correct.sum().float()))
+        res_h.copy_(res, non_blocking=False)       # device -> host read of loss and #correct
+        return res_h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_resident()
+        torch.cuda.synchronize(dev)
+        # ---- device-resident timed region (with per-kernel-class events and clock sampling) ----
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        lib.fgnn_profile_reset()
+        lib.fgnn_profile_enable(1)
+        lib.fgnn_reset_launch_count()
+        ms = timed(step_resident, args.steps)
+        launches = int(lib.fgnn_launch_count())
+        lib.fgnn_profile_enable(0)
+        if rank == 0:
+            sampler.stop_flag.set()
+            sampler.join(timeout=3)
+        import ctypes as C
+        kinds = {}
+        for kind, name in ((0, "tc_mlp_kernel"), (1, "tc_matmul_kernel"), (2, "plane_stats16_kernel")):
+            tot, cnt = C.c_double(0), C.c_int64(0)
+            lib.fgnn_profile_read(kind, C.byref(tot), C.byref(cnt))
+            kinds[name] = (tot.value, cnt.value)
+        # ---- end-to-end timed region ----
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    from oracle import fgnn_oracle as O
+    total_pairs = pairs * world * args.steps
+    value = total_pairs / (ms / 1e3)
+    e2e_value = total_pairs / (ms_e2e / 1e3)
+    flops_pair = O.flops_per_pair(cfg["n"], cfg["c"], cfg["blocks"], cfg["depth"])
+    f_conv, f_mm = O.flops_per_graph(cfg["n"], cfg["c"], cfg["blocks"], cfg["depth"])
+    graphs_per_step = 2 * pairs
+    kind_flops = {"tc_mlp_kernel": f_conv * graphs_per_step * args.steps,
+                  "tc_matmul_kernel": f_mm * graphs_per_step * args.steps}
+    kernels = {}
+    for name, (tot_ms, cnt) in kinds.items():
+        entry = {"launches": cnt, "total_ms": tot_ms, "share_of_step": tot_ms / ms if ms else None}
+        if name in kind_flops and tot_ms > 0:
+            entry["tflops"] = kind_flops[name] / (tot_ms / 1e3) / 1e12
+        kernels[name] = entry
+    dom = max(("tc_mlp_kernel", "tc_matmul_kernel"), key=lambda k: kinds[k][0])
+    roofline = None
+    if args.precision != "fp32" and kinds[dom][0] > 0:
+        achieved = kind_flops[dom] / (kinds[dom][0] / 1e3) / 1e12
+        peak = peaks["sustained"]
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']}); kernel timed inside a long step",
+                    "flops_per_launch": kind_flops[dom] / max(kinds[dom][1], 1),
+                    "avg_launch_ms": kinds[dom][0] / max(kinds[dom][1], 1)}
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": args.workload, "n": cfg["n"], "width": cfg["c"], "blocks": cfg["blocks"],
+                   "depth_of_mlp": cfg["depth"], "pairs_per_gpu": pairs, "global_pairs": pairs * world,
+                   "parallelism": f"dp{world} (pairs sharded, no forward collective)",
+                   "l2_policy": "inputs (256 MB/step/GPU) and activations (>10 GB/step/GPU) exceed the 126 MB L2"},
+        "whole_step_tflops": flops_pair * pairs * world * args.steps / (ms / 1e3) / 1e12,
+        "frac_of_bf16_peak_burst": flops_pair * pairs * args.steps / (ms / 1e3) / 1e12 / peaks["burst"],
+        "frac_of_bf16_peak_sustained": flops_pair * pairs * args.steps / (ms / 1e3) / 1e12 / peaks["sustained"],
+        "gpu_launches": launches,
+        "kernels": kernels,
+        "roofline": roofline,
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(x1_h.numel() * 4 * 2), "d2h_bytes_per_step": int(res_h.numel() * 4)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, sec = cpu_reference_rate(cfg, steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": f"2 timed + 1 warm-up forwards of 1 pair of the same workload "
+                                          f"({sec:.2f} s each), oracle port, fp32 torch CPU"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

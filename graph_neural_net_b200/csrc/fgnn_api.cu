@@ -3,9 +3,47 @@
 #include "fgnn_f32.cuh"
 #include "fgnn_tc.cuh"
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace fgnn {
 thread_local char g_last_error[512] = "";
 thread_local int64_t g_launches = 0;
+
+namespace prof {
+namespace {
+struct Pool {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t used = 0;
+};
+Pool g_pool[kNumKinds];
+bool g_enabled = false;
+std::mutex g_mu;
+constexpr size_t kMaxEvents = 1 << 16;
+}  // namespace
+void begin(Kind k, cudaStream_t st) {
+  if (!g_enabled) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Pool& p = g_pool[k];
+  if (p.used >= kMaxEvents) return;
+  if (p.used == p.ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    p.ev.emplace_back(a, b);
+  }
+  cudaEventRecord(p.ev[p.used].first, st);
+}
+void end(Kind k, cudaStream_t st) {
+  if (!g_enabled) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Pool& p = g_pool[k];
+  if (p.used >= p.ev.size()) return;
+  cudaEventRecord(p.ev[p.used].second, st);
+  ++p.used;
+}
+}  // namespace prof
 
 namespace {
 
@@ -233,6 +271,32 @@ int fgnn_debug_tc_mlp(int32_t precision, const fgnn_mlp_params* p, const float* 
                       void* stream) {
   FGNN_CHECK_ARG(p != nullptr, "null params");
   return tc::debug_mlp(precision, *p, x, y, G, N, n_per_graph, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+void fgnn_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(prof::g_mu);
+  prof::g_enabled = on != 0;
+}
+
+void fgnn_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(prof::g_mu);
+  for (auto& p : prof::g_pool) p.used = 0;
+}
+
+int fgnn_profile_read(int32_t kind, double* total_ms, int64_t* launches) {
+  FGNN_CHECK_ARG(kind >= 0 && kind < prof::kNumKinds && total_ms && launches, "bad kind %d", kind);
+  std::lock_guard<std::mutex> lk(prof::g_mu);
+  prof::Pool& p = prof::g_pool[kind];
+  double ms = 0.0;
+  for (size_t i = 0; i < p.used; ++i) {
+    FGNN_CUDA(cudaEventSynchronize(p.ev[i].second));
+    float t = 0.f;
+    FGNN_CUDA(cudaEventElapsedTime(&t, p.ev[i].first, p.ev[i].second));
+    ms += t;
+  }
+  *total_ms = ms;
+  *launches = (int64_t)p.used;
+  return FGNN_OK;
 }
 
 }  // extern "C"

@@ -42,6 +42,13 @@ inline int fail(int code, const char* fmt, ...) {
                           cudaGetErrorString(e__), __FILE__, __LINE__);                      \
   } while (0)
 
+// Optional per-kernel-class device timing (CUDA events on the launching stream); off by default.
+namespace prof {
+enum Kind { kMlp = 0, kMatmul = 1, kStats = 2, kGlue = 3, kNumKinds = 4 };
+void begin(Kind k, cudaStream_t st);
+void end(Kind k, cudaStream_t st);
+}  // namespace prof
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

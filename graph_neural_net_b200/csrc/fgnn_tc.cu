@@ -771,10 +771,12 @@ int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const f
     }                                                                                                    \
     tc_matmul_kernel<T, BNV><<<grid, 192, MatmulCfg<BNV>::kSmemBytes, st>>>(ma, mb, a);                   \
   } while (0)
+  prof::begin(prof::kMatmul, st);
   if (BN == 64) FGNN_MM_LAUNCH(64);
   else if (BN == 128) FGNN_MM_LAUNCH(128);
   else FGNN_MM_LAUNCH(256);
 #undef FGNN_MM_LAUNCH
+  prof::end(prof::kMatmul, st);
   FGNN_LAUNCHED();
   return FGNN_OK;
 }
@@ -834,7 +836,9 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, int N, int NP, const int32_t* npg
   long total_tiles = (long)G * ((Ppl + kTileM - 1) / kTileM);
   int grid = (int)std::min<long>((long)num_sms() * ctas_per_sm, total_tiles);
   if (grid < 1) grid = 1;
+  prof::begin(prof::kMlp, st);
   tc_mlp_kernel<T, COUT><<<grid, 160, smem, st>>>(mx0, mx1, mw1, mwh, a);
+  prof::end(prof::kMlp, st);
   FGNN_LAUNCHED();
   return FGNN_OK;
 }
@@ -849,8 +853,10 @@ int launch_mlp(const MlpLaunch<T>& L, int G, int N, int NP, const int32_t* npg, 
 template <typename T>
 int launch_stats(const T* y, const float* gw, const float* gb, float eps, float* coef, float* rsum, float* csum,
                  int G, int C, int N, int NP, const int32_t* npg, cudaStream_t st) {
+  prof::begin(prof::kStats, st);
   plane_stats16_kernel<T><<<G * C, 256, (size_t)8 * NP * sizeof(float), st>>>(y, gw, gb, eps, coef, rsum, csum, C, N,
                                                                               NP, npg);
+  prof::end(prof::kStats, st);
   FGNN_LAUNCHED();
   return FGNN_OK;
 }

@@ -160,6 +160,14 @@ int fgnn_embed_fwd(const fgnn_embed_params* p, int32_t precision, const float* x
 int64_t fgnn_launch_count(void);
 void fgnn_reset_launch_count(void);
 
+/* Per-kernel-class device timing for bench.py's roofline: when enabled, every launch of the class
+ * is bracketed by CUDA events on the launching stream.  kind: 0 = tensor-core conv-chain (MLP)
+ * kernel, 1 = tensor-core N x N matmul kernel, 2 = plane statistics, 3 = other glue kernels.
+ * fgnn_profile_read synchronises on the recorded events and returns their summed duration. */
+void fgnn_profile_enable(int on);
+void fgnn_profile_reset(void);
+int fgnn_profile_read(int32_t kind, double* total_ms, int64_t* launches);
+
 /* Diagnostics for the tensor-core building blocks (tests call these to check each kernel in
  * isolation against the fp32 operators): 16-bit planes are (G*C) planes of pitch_rows x pitch_cols. */
 int fgnn_debug_tc_matmul(int32_t precision, const float* a, const float* b, float* out, int32_t G,
