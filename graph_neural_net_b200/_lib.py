@@ -131,13 +131,16 @@ _workspaces = {}
 
 
 def workspace(device, nbytes: int) -> torch.Tensor:
-    """A reusable uint8 scratch tensor of at least nbytes on `device` (1 KiB aligned by torch)."""
+    """A reusable uint8 scratch tensor of at least nbytes on `device`, 1 KiB aligned (TMA / swizzled
+    shared-memory tiles want 1024-byte aligned bases; torch only guarantees 512)."""
     key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None
         _workspaces.pop(key, None)
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        raw = torch.empty(max(int(nbytes), 1 << 20) + 1024, dtype=torch.uint8, device=device)
+        off = (-raw.data_ptr()) % 1024
+        buf = raw[off:off + raw.numel() - 1024]
         _workspaces[key] = buf
     return buf
 

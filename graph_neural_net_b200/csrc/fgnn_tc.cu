@@ -1,19 +1,26 @@
 // Tensor-core path of libfgnn_b200 (FGNN_BF16 / FGNN_FP16): TMA-fed tcgen05 kernels with TMEM
 // accumulators for the two GEMM families of a 2-FGNN block, plus the small CUDA-core kernels
-// that glue them (statistics, weight folding, pooling).
+// that glue them (weight folding, statistics finalisation, pooling).
 //
-// Data layout (DESIGN.md "HBM layout"): every activation is a set of 16-bit planes
-//   act[g][c][i][j],  i < N rows, row pitch NP = round_up(N, 8) elements (16-byte rows for TMA),
-// holding the PRE-GraphNorm output of the MLP that produced it.  GraphNorm is never applied to a
-// stored tensor: its per-(graph, channel) scale a and shift s
-//   a = w / (2 sqrt(n (var + eps))),   s = beta - a * mean        (layers.py:68-80)
-// are folded into the consumer: into the first 1x1-conv weights of the next MLP
-// (W diag(a), b + W s), into the epilogue of the N x N matmul
-// ((a1 Y1 + s1 J)(a2 Y2 + s2 J) = a1 a2 Y1 Y2 + a1 s2 r1 1^T + s1 a2 1 c2^T + s1 s2 n J), and into the
-// final max-pool (max of a*y+s = a*max(y)+s or a*min(y)+s by the sign of a).
+// HBM layout (DESIGN.md "Data layout").  Every activation is a set of 16-bit planes holding the
+// PRE-GraphNorm output of the MLP that produced it.  GraphNorm is never applied to a stored tensor:
+// its per-(graph, channel) scale a and shift s
+//     a = w / (2 sqrt(n (var + eps))),   s = beta - a * mean                (layers.py:68-80)
+// are folded into the consumer: into the first 1x1-conv weights of the next MLP (W diag(a), b + W s),
+// into the epilogue of the N x N matmul
+//     (a1 Y1 + s1 J)(a2 Y2 + s2 J) = a1 a2 Y1 Y2 + a1 s2 r1 1^T + s1 a2 1 c2^T + s1 s2 n J,
+// and into the final max-pool (max(a y + s) = a max(y) + s or a min(y) + s by the sign of a).
+// The row sums r1 = Y1 1 and column sums c2 = 1^T Y2 come out of the matmul itself: the operand
+// layouts carry a row / column of ones per MMA tile,
+//   layout C (block inputs/outputs, Y2, mult): rows i < N, physical column pj = j + j / (BN-1), pitch
+//            NPC = BN * NT; physical columns pj % BN == BN-1 are "holes" (ones in Y2, zero elsewhere);
+//   layout A (Y1): physical row pi = i + i / 127, PRA = 128 * MT rows, pitch NPA = round_up(N, 8);
+//            physical rows pi % 128 == 127 hold ones,
+// so D[127, :] of every 128 x BN accumulator tile is c2 and D[:, BN-1] is r1, at no extra MMA cost.
 #include "fgnn_tc.cuh"
 #include "fgnn_ptx.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -24,52 +31,92 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kMaxN = 1024;   // plane_stats keeps column partials in registers
-constexpr int kTileM = 128;   // pixels per MLP tile / rows per matmul tile
+constexpr int kMaxN = 1024;
+constexpr int kTileM = 128;  // pixels per MLP tile / physical rows per matmul tile
+constexpr int kTM1 = 127;    // logical rows per matmul tile
+
+struct Geo {
+  int N, BN, TN1, NT, NPC, NPA, MT, PRA, BNLOG;
+  long PSC, PSA;
+};
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+Geo make_geo(int N) {
+  Geo g;
+  g.N = N;
+  g.BN = (N <= 63) ? 64 : (N <= 127 ? 128 : 256);
+  g.TN1 = g.BN - 1;
+  g.BNLOG = (g.BN == 64) ? 6 : (g.BN == 128 ? 7 : 8);
+  g.NT = (N + g.TN1 - 1) / g.TN1;
+  g.NPC = g.BN * g.NT;
+  g.NPA = round_up(N, 8);
+  g.MT = (N + kTM1 - 1) / kTM1;
+  g.PRA = 128 * g.MT;
+  g.PSC = (long)N * g.NPC;
+  g.PSA = (long)g.PRA * g.NPA;
+  return g;
+}
 
 __device__ __forceinline__ int graph_n(const int32_t* n_per_graph, int g, int N) {
   return n_per_graph ? n_per_graph[g] : N;
 }
-// rows of a plane that kernels must keep finite/zero so K-loops of the matmul may over-read
+// rows of a plane that the conv kernels must cover so that K-loops of the matmul may over-read zeros
 __device__ __forceinline__ int rows_cover(const int32_t* n_per_graph, int g, int N) {
   if (!n_per_graph) return N;
   int n = n_per_graph[g];
   int r = (n + 63) / 64 * 64;
   return r < N ? r : N;
 }
+__device__ __forceinline__ long mlp_tiles(const int32_t* n_per_graph, int g, const Geo& geo) {
+  return ((long)rows_cover(n_per_graph, g, geo.N) * geo.NPC + kTileM - 1) / kTileM;
+}
 
 // =============================================================================================
 // small CUDA-core kernels
 // =============================================================================================
 
-// fp32 (G,C,N,N) -> 16-bit planes (G,C,N,NP); padding and invalid positions written as zero
+// fp32 (G,C,N,N) -> 16-bit planes in layout C (mode 0) or layout A (mode 1).  Padding, holes and
+// the ones row/column are written as zero (only the debug entry points use layout A / ones-free C).
 template <typename T>
-__global__ void to_planes_kernel(const float* __restrict__ x, T* __restrict__ out, int C, int N, int NP,
+__global__ void to_planes_kernel(const float* __restrict__ x, T* __restrict__ out, int C, Geo geo, int mode,
                                  const int32_t* __restrict__ n_per_graph) {
   const int gc = blockIdx.y;
   const int g = gc / C;
-  const int n = graph_n(n_per_graph, g, N);
-  const long Ppl = (long)N * NP;
-  for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < Ppl; p += (long)gridDim.x * blockDim.x) {
-    int i = (int)(p / NP), j = (int)(p % NP);
-    float v = (i < n && j < n) ? x[((long)gc * N + i) * N + j] : 0.f;
-    out[(long)gc * Ppl + p] = Elem<T>::from_float(v);
+  const int n = graph_n(n_per_graph, g, geo.N);
+  const long PS = mode == 0 ? geo.PSC : geo.PSA;
+  const int pitch = mode == 0 ? geo.NPC : geo.NPA;
+  for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < PS; p += (long)gridDim.x * blockDim.x) {
+    int pi = (int)(p / pitch), pj = (int)(p % pitch);
+    int i, j;
+    bool hole;
+    if (mode == 0) {
+      hole = (pj % geo.BN) == geo.BN - 1;
+      i = pi;
+      j = pj - pj / geo.BN;
+    } else {
+      hole = (pi % 128) == 127;
+      i = pi - pi / 128;
+      j = pj;
+    }
+    float v = (!hole && i < n && j < n) ? x[((long)gc * geo.N + i) * geo.N + j] : 0.f;
+    out[(long)gc * PS + p] = Elem<T>::from_float(v);
   }
 }
 
-// 16-bit planes -> fp32 (G,C,N,N), optionally applying y = a*v + s on valid positions (debug / tests)
+// layout C planes -> fp32 (G,C,N,N), optionally y = a*v + s on valid positions (debug / tests)
 template <typename T>
 __global__ void from_planes_kernel(const T* __restrict__ in, float* __restrict__ out, const float* __restrict__ coef,
-                                   int C, int N, int NP, const int32_t* __restrict__ n_per_graph) {
+                                   int C, Geo geo, const int32_t* __restrict__ n_per_graph) {
   const int gc = blockIdx.y;
   const int g = gc / C;
-  const int n = graph_n(n_per_graph, g, N);
+  const int n = graph_n(n_per_graph, g, geo.N);
   const float a = coef ? coef[2 * gc] : 1.f, s = coef ? coef[2 * gc + 1] : 0.f;
-  const long P = (long)N * N;
+  const long P = (long)geo.N * geo.N;
   for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long)gridDim.x * blockDim.x) {
-    int i = (int)(p / N), j = (int)(p % N);
+    int i = (int)(p / geo.N), j = (int)(p % geo.N);
     float v = 0.f;
-    if (i < n && j < n) v = a * Elem<T>::to_float(in[((long)gc * N + i) * NP + j]) + s;
+    if (i < n && j < n) v = a * Elem<T>::to_float(in[(long)gc * geo.PSC + (long)i * geo.NPC + j + j / geo.TN1]) + s;
     out[(long)gc * P + p] = v;
   }
 }
@@ -83,140 +130,96 @@ __global__ void convert_weight_kernel(const float* __restrict__ w, T* __restrict
   out[idx] = Elem<T>::from_float(k < ci ? w[o * ci + k] : 0.f);
 }
 
-// Per-graph folded first-layer weights.  Source s contributes channels [0,c_s) placed at K offset
-// koff_s (K padded to multiples of 16 per source, whole row padded to K1g, a multiple of 64).
-//   Wf[g][co][koff_s + ch] = W[co][col_s + ch] * a_s[g][ch]
-//   bf[g][co]              = b[co] + sum_s sum_ch W[co][col_s + ch] * s_s[g][ch]
+// Per-graph folded first-layer weights for up to two MLPs that share their input (mlp1/mlp2).
+//   Wf[g][m][co][koff_s + ch] = W_m[co][col_s + ch] * a_s[g][ch]
+//   bf[g][m][co]              = b_m[co] + sum_s sum_ch W_m[co][col_s + ch] * s_s[g][ch]
 struct FoldArgs {
-  const float* w;        // (c_out, c0 + c1)
-  const float* b;        // (c_out)
-  const float* coef[2];  // [G][c_s][2] or null (identity)
-  int c[2], koff[2], nsrc;
+  const float* w[2];     // per MLP: (c_out, c0 + c1)
+  const float* b[2];     // per MLP: (c_out)
+  const float* coef[2];  // per source: [G][c_s][2] or null (identity)
+  int c[2], koff[2], nsrc, nmlp;
   int c_out, K1g;
 };
 template <typename T>
 __global__ void fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf) {
   const int g = blockIdx.x;
   const int cin = a.c[0] + (a.nsrc > 1 ? a.c[1] : 0);
-  T* wg = wf + (long)g * a.c_out * a.K1g;
-  for (int idx = threadIdx.x; idx < a.c_out * a.K1g; idx += blockDim.x) {
-    int co = idx / a.K1g, k = idx % a.K1g;
-    float v = 0.f;
-    int col = 0;
-    for (int s = 0; s < a.nsrc; ++s) {
-      int ch = k - a.koff[s];
-      if (ch >= 0 && ch < a.c[s]) {
-        float sc = a.coef[s] ? a.coef[s][((long)g * a.c[s] + ch) * 2] : 1.f;
-        v = a.w[co * cin + col + ch] * sc;
+  for (int m = 0; m < a.nmlp; ++m) {
+    T* wg = wf + ((long)g * a.nmlp + m) * a.c_out * a.K1g;
+    const float* w = a.w[m];
+    for (int idx = threadIdx.x; idx < a.c_out * a.K1g; idx += blockDim.x) {
+      int co = idx / a.K1g, k = idx % a.K1g;
+      float v = 0.f;
+      int col = 0;
+      for (int s = 0; s < a.nsrc; ++s) {
+        int ch = k - a.koff[s];
+        if (ch >= 0 && ch < a.c[s]) {
+          float sc = a.coef[s] ? a.coef[s][((long)g * a.c[s] + ch) * 2] : 1.f;
+          v = w[co * cin + col + ch] * sc;
+        }
+        col += a.c[s];
       }
-      col += a.c[s];
+      wg[idx] = Elem<T>::from_float(v);
     }
-    wg[idx] = Elem<T>::from_float(v);
-  }
-  for (int co = threadIdx.x; co < a.c_out; co += blockDim.x) {
-    float acc = a.b[co];
-    int col = 0;
-    for (int s = 0; s < a.nsrc; ++s) {
-      if (a.coef[s])
-        for (int ch = 0; ch < a.c[s]; ++ch)
-          acc = fmaf(a.w[co * cin + col + ch], a.coef[s][((long)g * a.c[s] + ch) * 2 + 1], acc);
-      col += a.c[s];
+    for (int co = threadIdx.x; co < a.c_out; co += blockDim.x) {
+      float acc = a.b[m][co];
+      int col = 0;
+      for (int s = 0; s < a.nsrc; ++s) {
+        if (a.coef[s])
+          for (int ch = 0; ch < a.c[s]; ++ch)
+            acc = fmaf(w[co * cin + col + ch], a.coef[s][((long)g * a.c[s] + ch) * 2 + 1], acc);
+        col += a.c[s];
+      }
+      bf[((long)g * a.nmlp + m) * a.c_out + co] = acc;
     }
-    bf[(long)g * a.c_out + co] = acc;
   }
 }
 
-// Per-plane statistics of a stored pre-norm plane over its valid n x n corner:
-//   coef[q] = {a, s} (GraphNorm scale/shift), rsum[q][i] = sum_j y[i][j], csum[q][j] = sum_i y[i][j].
-template <typename T>
-__global__ void __launch_bounds__(256)
-plane_stats16_kernel(const T* __restrict__ y, const float* __restrict__ gw, const float* __restrict__ gb,
-                     float eps, float* __restrict__ coef, float* __restrict__ rsum, float* __restrict__ csum,
-                     int C, int N, int NP, const int32_t* __restrict__ n_per_graph) {
-  extern __shared__ float sh_col[];  // [8][NP]
-  const int q = blockIdx.x;
-  const int g = q / C, c = q % C;
-  const int n = graph_n(n_per_graph, g, N);
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const T* yp = y + (long)q * N * NP;
-  float colacc[kMaxN / 64][2];
-#pragma unroll
-  for (int t = 0; t < kMaxN / 64; ++t) colacc[t][0] = colacc[t][1] = 0.f;
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = warp; i < n; i += 8) {
-    const T* row = yp + (long)i * NP;
-    float rs = 0.f;
-#pragma unroll
-    for (int t = 0; t < kMaxN / 64; ++t) {
-      int j = t * 64 + lane * 2;
-      if (j < n) {
-        float v0 = Elem<T>::to_float(row[j]);
-        float v1 = (j + 1 < n) ? Elem<T>::to_float(row[j + 1]) : 0.f;
-        colacc[t][0] += v0;
-        colacc[t][1] += v1;
-        rs += v0 + v1;
-        s2 = fmaf(v0, v0, fmaf(v1, v1, s2));
-      }
-    }
-    s1 += rs;
-    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-    if (lane == 0 && rsum) rsum[(long)q * N + i] = rs;
-  }
-  if (rsum)
-    for (int i = n + threadIdx.x; i < N; i += blockDim.x) rsum[(long)q * N + i] = 0.f;
-#pragma unroll
-  for (int t = 0; t < kMaxN / 64; ++t) {
-    int j = t * 64 + lane * 2;
-    if (j < NP) {
-      sh_col[warp * NP + j] = colacc[t][0];
-      if (j + 1 < NP) sh_col[warp * NP + j + 1] = colacc[t][1];
-    }
-  }
-  __shared__ double red[2][8];
-  double d1 = s1, d2 = s2;
-  for (int o = 16; o > 0; o >>= 1) {
-    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-  }
-  if (lane == 0) { red[0][warp] = d1; red[1][warp] = d2; }
-  __syncthreads();
-  if (csum)
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-      float t = 0.f;
-      if (j < n)
-        for (int w = 0; w < 8; ++w) t += sh_col[w * NP + j];
-      csum[(long)q * N + j] = t;
-    }
-  if (threadIdx.x == 0) {
-    double S = 0, SS = 0;
-    for (int w = 0; w < 8; ++w) { S += red[0][w]; SS += red[1][w]; }
-    double cnt = (double)n * n;
-    double mean = S / cnt;
-    double var = SS / cnt - mean * mean;
-    if (var < 0) var = 0;
-    double a = (double)(gw ? gw[c] : 1.f) / (2.0 * sqrt((double)n * (var + (double)eps)));
-    coef[2 * q] = (float)a;
-    coef[2 * q + 1] = (float)((double)(gb ? gb[c] : 0.f) - a * mean);
-  }
+// (sum, sum of squares) accumulated by the conv-chain epilogue -> GraphNorm scale / shift.
+//   acc[g][m][c][2] (double)  ->  coef_m[g][c] = {a, s}
+struct CoefArgs {
+  const double* acc;
+  float* coef[2];
+  const float* gw[2];
+  const float* gb[2];
+  float eps[2];
+  int nmlp, C, N;
+  const int32_t* n_per_graph;
+};
+__global__ void finalize_coef_kernel(CoefArgs a, int total) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int c = idx % a.C;
+  int m = (idx / a.C) % a.nmlp;
+  int g = idx / (a.C * a.nmlp);
+  const int n = graph_n(a.n_per_graph, g, a.N);
+  const double cnt = (double)n * n;
+  const double S = a.acc[2 * (long)idx], SS = a.acc[2 * (long)idx + 1];
+  const double mean = S / cnt;
+  double var = SS / cnt - mean * mean;
+  if (var < 0) var = 0;
+  const double sc = (double)(a.gw[m] ? a.gw[m][c] : 1.f) / (2.0 * sqrt((double)n * (var + (double)a.eps[m])));
+  a.coef[m][((long)g * a.C + c) * 2] = (float)sc;
+  a.coef[m][((long)g * a.C + c) * 2 + 1] = (float)((double)(a.gb[m] ? a.gb[m][c] : 0.f) - sc * mean);
 }
 
-// emb[g][c][i] = max_{j<n} (a*y[i][j] + s); rows >= n -> 0   (layers.py:194-203 on folded data)
+// emb[g][c][i] = max_{j<n} (a*y[i][j] + s); rows >= n -> 0   (layers.py:194-203 on folded data, layout C)
 template <typename T>
 __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ coef, float* __restrict__ emb, int C,
-                            int N, int NP, long rows, const int32_t* __restrict__ n_per_graph) {
+                            Geo geo, long rows, const int32_t* __restrict__ n_per_graph) {
   const long row = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   if (row >= rows) return;
   const int lane = threadIdx.x % 32;
-  const int i = (int)(row % N);
-  const long q = row / N;
+  const int i = (int)(row % geo.N);
+  const long q = row / geo.N;
   const int g = (int)(q / C);
-  const int n = graph_n(n_per_graph, g, N);
+  const int n = graph_n(n_per_graph, g, geo.N);
   float out = 0.f;
   if (i < n) {
-    const T* r = y + (q * N + i) * NP;
+    const T* r = y + q * geo.PSC + (long)i * geo.NPC;
     float mx = -INFINITY, mn = INFINITY;
     for (int j = lane; j < n; j += 32) {
-      float v = Elem<T>::to_float(r[j]);
+      float v = Elem<T>::to_float(r[j + j / geo.TN1]);
       mx = fmaxf(mx, v);
       mn = fminf(mn, v);
     }
@@ -231,72 +234,89 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ c
 }
 
 // =============================================================================================
-// K_A: fused conv chain on tensor cores.
-//   tile  = 128 consecutive pixels of one graph (flattened N x NP plane), all channels
-//   layer1: D[128 px, COUT] = X[px, K1] * W1f[g]^T     A = TMA-staged smem (MN-major), B = smem (K-major)
-//   layer>=2: D = relu(D + b) (16-bit, written back to TMEM) * W^T   A = TMEM, B = smem
-//   output: raw last-layer accumulators as 16-bit planes (its bias cancels in GraphNorm).
-// Warp roles: warp 0 = TMA producer + MMA issuer (one elected lane), warps 1-4 = TMEM epilogue.
+// K_A: fused conv chains on tensor cores, software-pipelined over kSlots tiles in flight.
+//   tile  = 128 consecutive physical pixels (layout C) of one graph, all channels; NMLP (1 or 2) MLPs
+//           consume the same staged input tile ("virtual tiles" v = tile * NMLP + m)
+//   layer1: D[128 px, COUT] = X[px, K1] * W1f[g][m]^T   A = TMA-staged smem (MN-major), B = smem (K-major)
+//   layer>=2: D = relu(D + b) (16-bit, written back to TMEM) * W^T        A = TMEM, B = smem
+//   output: raw last-layer accumulators as 16-bit planes (the last bias cancels in GraphNorm), their
+//           per-(graph, channel) sum and sum of squares (fp32 in registers, double atomics per flush).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups that
+// alternate virtual tiles (slot parity).  TMEM slot s: accumulator columns [s*1.5*COUT, +COUT),
+// packed hidden activations in the next COUT/2 columns.
 // =============================================================================================
+enum OutMode { kOutC = 0, kOutA = 1 };
+
 template <typename T>
 struct MlpArgs {
-  int G, N, NP;
-  long Ppl;
+  int G;
+  Geo geo;
   int k_src[2], nsrc, K1, K1g;
   int depth, Kh;
-  const float* bias1;                   // [G][COUT] folded layer-1 bias
-  const float* bias[FGNN_MAX_DEPTH];    // layer l >= 1 biases
-  T* out;                               // [G][COUT][N][NP]
+  const float* bias1;                        // [G][NMLP][COUT] folded layer-1 bias
+  const float* bias[2][FGNN_MAX_DEPTH];      // per MLP, layer l >= 1 biases
+  T* out[2];                                 // per MLP output planes
+  int out_mode[2];                           // kOutC / kOutA
+  int ones[2];                               // write the ones row/column (Y1 / Y2) instead of zeros
+  double* stat_acc;                          // [G][NMLP][COUT][2]
   const int32_t* n_per_graph;
 };
 
-template <int COUT>
+constexpr int kSlots = 4;
+constexpr int kInStages = 4;
+
+template <int COUT, int NMLP>
 struct MlpSmem {
-  static constexpr int kStages = 2;
   static size_t bytes(int K1, int K1g, int depth, int Kh) {
-    return 1024 + (size_t)kStages * K1 * 256 + (size_t)K1g * COUT * 2 + (size_t)(depth - 1) * Kh * COUT * 2 + 256;
+    return 1024 + (size_t)kInStages * K1 * 256 + (size_t)2 * NMLP * K1g * COUT * 2 +
+           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + 512;
   }
 };
 
-template <typename T, int COUT>
-__global__ void __launch_bounds__(160)
+template <typename T, int COUT, int NMLP>
+__global__ void __launch_bounds__(320, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
               const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wh,
               const MlpArgs<T> args) {
-  constexpr int kStages = MlpSmem<COUT>::kStages;
-  constexpr uint32_t kTmemCols = (COUT * 3 / 2 <= 64) ? 64 : (COUT * 3 / 2 <= 128 ? 128 : 256);
-  constexpr int kHCol = COUT;  // TMEM column where the packed 16-bit hidden activations start
+  constexpr int kSlotW = COUT * 3 / 2;
+  constexpr int kQCol = kSlots * kSlotW;   // sum-of-squares accumulators live in TMEM: [kQCol + eg*COUT, +COUT)
+  constexpr uint32_t kTmemCols = (kQCol + 2 * COUT <= 256) ? 256 : 512;
+  static_assert(kQCol + 2 * COUT <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int K1 = args.K1, K1g = args.K1g, depth = args.depth, Kh = args.Kh;
+  const Geo geo = args.geo;
   const uint32_t stage_bytes = (uint32_t)K1 * 256u;
+  const uint32_t w1_mlp_bytes = (uint32_t)K1g * COUT * 2u;     // one MLP's folded first-layer weights
+  const uint32_t w1_buf_bytes = w1_mlp_bytes * NMLP;           // one graph's
+  const uint32_t wh_mat_bytes = (uint32_t)Kh * COUT * 2u;
   uint8_t* s_in = smem;
-  uint8_t* s_w1 = s_in + (size_t)kStages * stage_bytes;
-  uint8_t* s_wh = s_w1 + (size_t)K1g * COUT * 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wh + (size_t)(depth - 1) * Kh * COUT * 2);
-  uint64_t* in_full = bars;              // [kStages]
-  uint64_t* in_empty = bars + kStages;   // [kStages]
-  uint64_t* w1_full = bars + 2 * kStages;
-  uint64_t* wh_full = w1_full + 1;
-  uint64_t* mma_done = wh_full + 1;
-  uint64_t* h_ready = mma_done + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
+  uint8_t* s_w1 = s_in + (size_t)kInStages * stage_bytes;      // [2 buffers][NMLP][atoms][COUT][128B]
+  uint8_t* s_wh = s_w1 + (size_t)2 * w1_buf_bytes;             // [NMLP][depth-1][atoms][COUT][128B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes);
+  uint64_t* in_full = bars;                   // [kInStages]
+  uint64_t* in_empty = in_full + kInStages;   // [kInStages]
+  uint64_t* w1_full = in_empty + kInStages;   // [2]
+  uint64_t* w1_empty = w1_full + 2;           // [2]
+  uint64_t* wh_full = w1_empty + 2;           // [1]
+  uint64_t* mma_done = wh_full + 1;           // [kSlots]
+  uint64_t* h_ready = mma_done + kSlots;      // [kSlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + kSlots);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 
   // ---- tile range of this CTA: contiguous chunk of the flat (graph, tile) list ----------------
   long total = 0;
-  for (int g = 0; g < args.G; ++g)
-    total += ((long)rows_cover(args.n_per_graph, g, args.N) * args.NP + kTileM - 1) / kTileM;
+  for (int g = 0; g < args.G; ++g) total += mlp_tiles(args.n_per_graph, g, geo);
   const long t_begin = total * blockIdx.x / gridDim.x;
   const long t_end = total * (blockIdx.x + 1) / gridDim.x;
+  const long V = (t_end - t_begin) * NMLP;  // virtual tiles of this CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
-    mbar_init(w1_full, 1);
+    for (int s = 0; s < kInStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
     mbar_init(wh_full, 1);
-    mbar_init(mma_done, 1);
-    mbar_init(h_ready, 4);
+    for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&h_ready[s], 4); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
@@ -305,160 +325,309 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // graph walker shared by all roles: flat tile t -> (graph g, first pixel p0); t must not decrease
+  struct Walker {
+    int g = 0;
+    long base = 0, tiles = 0;
+  };
+  auto walker_init = [&](Walker& w) {
+    w.g = 0;
+    w.base = 0;
+    w.tiles = mlp_tiles(args.n_per_graph, 0, geo);
+  };
+  auto walker_seek = [&](Walker& w, long t) {
+    while (t >= w.base + w.tiles) {
+      w.base += w.tiles;
+      ++w.g;
+      w.tiles = mlp_tiles(args.n_per_graph, w.g, geo);
+    }
+  };
+
+
   if (warp == 0) {
-    if (lane == 0 && t_begin < t_end) {
-      // ================= producer + MMA issuer (single thread) =================
+    if (lane == 0 && V > 0) {
+      // ================= TMA producer =================
       prefetch_tensormap(&map_x0);
       prefetch_tensormap(&map_w1);
       if (depth > 1) {
         const int atoms = Kh / 64;
-        mbar_arrive_expect_tx(wh_full, (uint32_t)((depth - 1) * Kh * COUT * 2));
-        for (int l = 0; l < depth - 1; ++l)
-          for (int at = 0; at < atoms; ++at)
-            tma_load_3d(s_wh + ((size_t)l * atoms + at) * COUT * 128, &map_wh, wh_full, at * 64, 0, l);
+        mbar_arrive_expect_tx(wh_full, (uint32_t)(NMLP * (depth - 1)) * wh_mat_bytes);
+        for (int m = 0; m < NMLP; ++m)
+          for (int l = 0; l < depth - 1; ++l)
+            for (int at = 0; at < atoms; ++at)
+              tma_load_3d(s_wh + ((size_t)(m * (depth - 1) + l) * atoms + at) * COUT * 128, &map_wh, wh_full, at * 64,
+                          0, m * (depth - 1) + l);
       }
-      // walk to the first tile
-      int g = 0;
-      long gbase = 0;
-      long gtiles = ((long)rows_cover(args.n_per_graph, 0, args.N) * args.NP + kTileM - 1) / kTileM;
-      auto seek = [&](long t) {
-        while (t >= gbase + gtiles) {
-          gbase += gtiles;
-          ++g;
-          gtiles = ((long)rows_cover(args.n_per_graph, g, args.N) * args.NP + kTileM - 1) / kTileM;
+      Walker w;
+      walker_init(w);
+      int cur_g = -1, nchg = 0;
+      uint32_t ph_w1e[2] = {0, 0}, ph_ine[kInStages];
+      for (int s = 0; s < kInStages; ++s) ph_ine[s] = 0;
+      for (long t = t_begin; t < t_end; ++t) {
+        walker_seek(w, t);
+        if (w.g != cur_g) {
+          const int b = nchg & 1;
+          if (nchg >= 2) { mbar_wait(&w1_empty[b], ph_w1e[b]); ph_w1e[b] ^= 1; }
+          mbar_arrive_expect_tx(&w1_full[b], w1_buf_bytes);
+          for (int m = 0; m < NMLP; ++m)
+            for (int at = 0; at < K1g / 64; ++at)
+              tma_load_3d(s_w1 + (size_t)b * w1_buf_bytes + (size_t)m * w1_mlp_bytes + (size_t)at * COUT * 128,
+                          &map_w1, &w1_full[b], at * 64, 0, w.g * NMLP + m);
+          cur_g = w.g;
+          ++nchg;
         }
-      };
-      auto issue_load = [&](long t, int stage) {
-        seek(t);
-        const int p0 = (int)((t - gbase) * kTileM);
-        uint8_t* dst = s_in + (size_t)stage * stage_bytes;
-        mbar_arrive_expect_tx(&in_full[stage], stage_bytes);
+        const long seq = t - t_begin;
+        const int st = (int)(seq % kInStages);
+        if (seq >= kInStages) { mbar_wait(&in_empty[st], ph_ine[st]); ph_ine[st] ^= 1; }
+        const int p0 = (int)((t - w.base) * kTileM);
+        uint8_t* dst = s_in + (size_t)st * stage_bytes;
+        mbar_arrive_expect_tx(&in_full[st], stage_bytes);
         for (int u = 0; u < 2; ++u) {
-          tma_load_3d(dst + (size_t)u * K1 * 128, &map_x0, &in_full[stage], p0 + u * 64, 0, g);
+          tma_load_3d(dst + (size_t)u * K1 * 128, &map_x0, &in_full[st], p0 + u * 64, 0, w.g);
           if (args.nsrc > 1)
-            tma_load_3d(dst + (size_t)u * K1 * 128 + (size_t)args.k_src[0] * 128, &map_x1, &in_full[stage],
-                        p0 + u * 64, 0, g);
+            tma_load_3d(dst + (size_t)u * K1 * 128 + (size_t)args.k_src[0] * 128, &map_x1, &in_full[st], p0 + u * 64,
+                        0, w.g);
         }
-      };
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && V > 0) {
+      // ================= MMA issuer =================
       const uint32_t idesc1 = make_idesc(Elem<T>::kFmt, /*A MN-major*/ 1, /*B K-major*/ 0, kTileM, COUT);
       const uint32_t idesc2 = make_idesc(Elem<T>::kFmt, 0, 0, kTileM, COUT);
-      uint32_t ph_in_full[kStages] = {0, 0}, ph_in_empty[kStages] = {0, 0};
-      uint32_t ph_w1 = 0, ph_h = 0;
-      int cur_g = -1;
-      // save/restore of the walker state around look-ahead loads
-      issue_load(t_begin, 0);
-      int g_cur_tile = g;
-      long gbase_cur = gbase, gtiles_cur = gtiles;
+      Walker w;
+      walker_init(w);
+      int cur_g = -1, nchg = 0, wbuf = 0;
+      uint32_t ph_w1f[2] = {0, 0}, ph_inf[kInStages], ph_h[kSlots];
+      for (int s = 0; s < kInStages; ++s) ph_inf[s] = 0;
+      for (int s = 0; s < kSlots; ++s) ph_h[s] = 0;
       if (depth > 1) mbar_wait(wh_full, 0);
-      for (long t = t_begin; t < t_end; ++t) {
-        const int stage = (int)((t - t_begin) % kStages);
-        // restore walker for the current tile, then prefetch the next one
-        g = g_cur_tile; gbase = gbase_cur; gtiles = gtiles_cur;
-        seek(t);
-        const int tg = g;
-        g_cur_tile = g; gbase_cur = gbase; gtiles_cur = gtiles;
-        if (tg != cur_g) {  // (re)load this graph's folded first-layer weights
-          mbar_arrive_expect_tx(w1_full, (uint32_t)(K1g * COUT * 2));
-          for (int at = 0; at < K1g / 64; ++at)
-            tma_load_3d(s_w1 + (size_t)at * COUT * 128, &map_w1, w1_full, at * 64, 0, tg);
-          mbar_wait(w1_full, ph_w1);
-          ph_w1 ^= 1;
-          cur_g = tg;
-        }
-        if (t + 1 < t_end) {
-          const int ns = (int)((t + 1 - t_begin) % kStages);
-          if (t + 1 - t_begin >= kStages) {  // stage was used before: wait for its MMAs to retire
-            mbar_wait(&in_empty[ns], ph_in_empty[ns]);
-            ph_in_empty[ns] ^= 1;
+      for (long v0 = 0; v0 < V; v0 += kSlots) {
+        for (int l = 0; l < depth; ++l) {
+          for (int s = 0; s < kSlots; ++s) {
+            const long v = v0 + s;
+            if (v >= V) break;
+            const long seq = v / NMLP;
+            const int m = (int)(v % NMLP);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
+            if (l == 0) {
+              const int st = (int)(seq % kInStages);
+              if (m == 0) {
+                walker_seek(w, t_begin + seq);
+                if (w.g != cur_g) {
+                  if (cur_g >= 0) mma_commit(&w1_empty[wbuf]);  // all MMAs that read the old buffer retire first
+                  wbuf = nchg & 1;
+                  mbar_wait(&w1_full[wbuf], ph_w1f[wbuf]);
+                  ph_w1f[wbuf] ^= 1;
+                  cur_g = w.g;
+                  ++nchg;
+                }
+                mbar_wait(&in_full[st], ph_inf[st]);
+                ph_inf[st] ^= 1;
+              }
+              if (v >= kSlots) {  // slot reuse: previous occupant's accumulator must be drained
+                mbar_wait(&h_ready[s], ph_h[s]);
+                ph_h[s] ^= 1;
+              }
+              tc_fence_after();
+              const uint32_t a_base = smem_u32(s_in + (size_t)st * stage_bytes);
+              const uint32_t w1_base = smem_u32(s_w1 + (size_t)wbuf * w1_buf_bytes + (size_t)m * w1_mlp_bytes);
+              for (int k = 0; k < K1 / 16; ++k) {
+                const uint64_t ad = smem_desc_sw128(a_base + (uint32_t)k * 2048u, (uint32_t)K1 * 128u, 1024u);
+                const uint64_t bd = smem_desc_sw128(w1_base + (uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u,
+                                                    16u, 1024u);
+                mma_ss(d_tmem, ad, bd, idesc1, k > 0 ? 1u : 0u);
+              }
+              if (m == NMLP - 1) mma_commit(&in_empty[st]);
+              mma_commit(&mma_done[s]);
+            } else {
+              mbar_wait(&h_ready[s], ph_h[s]);
+              ph_h[s] ^= 1;
+              tc_fence_after();
+              const uint32_t wl = smem_u32(s_wh + (size_t)(m * (depth - 1) + (l - 1)) * wh_mat_bytes);
+              for (int k = 0; k < COUT / 16; ++k) {
+                const uint64_t bd = smem_desc_sw128(wl + (uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u,
+                                                    16u, 1024u);
+                mma_ts(d_tmem, d_tmem + COUT + (uint32_t)k * 8u, bd, idesc2, k > 0 ? 1u : 0u);
+              }
+              mma_commit(&mma_done[s]);
+            }
           }
-          issue_load(t + 1, ns);
         }
-        // ---- layer 1: SS MMA over K1 ----
-        mbar_wait(&in_full[stage], ph_in_full[stage]);
-        ph_in_full[stage] ^= 1;
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(s_in + (size_t)stage * stage_bytes);
-        const uint32_t w1_base = smem_u32(s_w1);
-        for (int s = 0; s < K1 / 16; ++s) {
-          const uint64_t ad = smem_desc_sw128(a_base + (uint32_t)s * 2048u, (uint32_t)K1 * 128u, 1024u);
-          const uint64_t bd = smem_desc_sw128(w1_base + (uint32_t)(s / 4) * (COUT * 128u) + (uint32_t)(s % 4) * 32u,
-                                              16u, 1024u);
-          mma_ss(tmem_base, ad, bd, idesc1, s > 0 ? 1u : 0u);
-        }
-        mma_commit(&in_empty[stage]);
-        mma_commit(mma_done);
-        // ---- layers 2..depth: A = packed hidden activations in TMEM ----
-        for (int l = 1; l < depth; ++l) {
-          mbar_wait(h_ready, ph_h);
-          ph_h ^= 1;
-          tc_fence_after();
-          const uint32_t wl = smem_u32(s_wh + (size_t)(l - 1) * Kh * COUT * 2);
-          for (int s = 0; s < COUT / 16; ++s) {
-            const uint64_t bd = smem_desc_sw128(wl + (uint32_t)(s / 4) * (COUT * 128u) + (uint32_t)(s % 4) * 32u,
-                                                16u, 1024u);
-            mma_ts(tmem_base, tmem_base + kHCol + (uint32_t)s * 8u, bd, idesc2, s > 0 ? 1u : 0u);
-          }
-          mma_commit(mma_done);
-        }
-        // accumulator must be drained before the next tile overwrites it
-        mbar_wait(h_ready, ph_h);
-        ph_h ^= 1;
       }
     }
   } else {
-    // ================= epilogue warps (TMEM lane quadrant = warp % 4) =================
-    const int quad = warp % 4;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    // ================= epilogue groups =================
+    const int eg = (warp - 2) / 4;           // 0: slots 0,2   1: slots 1,3
+    const int quad = warp % 4;               // TMEM lane quadrant this warp may access
     const int pix_in_tile = quad * 32 + lane;
-    uint32_t ph_mma = 0;
-    int g = 0;
-    long gbase = 0;
-    long gtiles = ((long)rows_cover(args.n_per_graph, 0, args.N) * args.NP + kTileM - 1) / kTileM;
-    for (long t = t_begin; t < t_end; ++t) {
-      while (t >= gbase + gtiles) {
-        gbase += gtiles;
-        ++g;
-        gtiles = ((long)rows_cover(args.n_per_graph, g, args.N) * args.NP + kTileM - 1) / kTileM;
-      }
-      const long p = (t - gbase) * kTileM + pix_in_tile;
-      const int n = graph_n(args.n_per_graph, g, args.N);
-      const int pi = (int)(p / args.NP), pj = (int)(p % args.NP);
-      const bool in_plane = p < args.Ppl;
-      const bool valid = in_plane && pi < n && pj < n;
-      for (int l = 0; l < depth; ++l) {
-        mbar_wait(mma_done, ph_mma);
-        ph_mma ^= 1;
-        tc_fence_after();
-        const bool last = (l == depth - 1);
-        const float* bias = (l == 0) ? (args.bias1 + (long)g * COUT) : args.bias[l];
+    uint32_t ph_mma[kSlots];
+    for (int s = 0; s < kSlots; ++s) ph_mma[s] = 0;
+    // per-thread statistics over the pixels this thread has seen: sums in registers, sums of squares in
+    // this thread's TMEM lane (keeps the epilogue inside the 168-register budget of a 10-warp CTA)
+    float acc_s[COUT];
+    const uint32_t q_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kQCol + eg * COUT);
+    {
+      uint32_t z[16];
 #pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(lane_addr + (uint32_t)c0, r);
-          tmem_wait_ld();
-          if (!last) {
-            uint32_t h[16];
+      for (int u = 0; u < 16; ++u) z[u] = 0u;
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c0 + 2 * u));
-              float v0 = fmaxf(__uint_as_float(r[2 * u]) + b2.x, 0.f);
-              float v1 = fmaxf(__uint_as_float(r[2 * u + 1]) + b2.y, 0.f);
-              h[u] = Elem<T>::pack(v0, v1);
-            }
-            tmem_st16(lane_addr + (uint32_t)kHCol + (uint32_t)(c0 / 2), h);
-          } else if (in_plane) {
-            T* op = args.out + ((long)g * COUT + c0) * args.Ppl + p;
+      for (int c0 = 0; c0 < COUT; c0 += 16) tmem_st16(q_addr + (uint32_t)c0, z);
+      tmem_wait_st();
+    }
 #pragma unroll
-            for (int u = 0; u < 32; ++u)
-              op[(long)u * args.Ppl] = Elem<T>::from_float(valid ? __uint_as_float(r[u]) : 0.f);
+    for (int c = 0; c < COUT; ++c) acc_s[c] = 0.f;
+    int acc_g = -1, acc_m = 0;
+    Walker w;
+    walker_init(w);
+    int slot_g[kSlots / 2] = {0, 0};
+    long slot_base[kSlots / 2] = {0, 0};
+
+    auto flush_stats = [&]() {
+      if (acc_g < 0) return;
+      double* dst = args.stat_acc + ((long)acc_g * NMLP + acc_m) * COUT * 2;
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t qq[16];
+        tmem_ld16(q_addr + (uint32_t)c0, qq);
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          float a = acc_s[c0 + u], q = __uint_as_float(qq[u]);
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
           }
+          if (lane == ((c0 + u) & 31)) {
+            atomicAdd(dst + 2 * (c0 + u), (double)a);
+            atomicAdd(dst + 2 * (c0 + u) + 1, (double)q);
+          }
+          acc_s[c0 + u] = 0.f;
+          qq[u] = 0u;
         }
-        if (!last) tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h_ready);
+        tmem_st16(q_addr + (uint32_t)c0, qq);
+      }
+      tmem_wait_st();
+    };
+
+    for (long v0 = 0; v0 < V; v0 += kSlots) {
+      for (int l = 0; l < depth; ++l) {
+        for (int s = eg; s < kSlots; s += 2) {
+          const long v = v0 + s;
+          if (v >= V) break;
+          const long seq = v / NMLP;
+          const int m = (int)(v % NMLP);
+          const bool last = (l == depth - 1);
+          const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * kSlotW);
+          // the walker only moves forward: resolve (graph, first tile of graph) once per virtual tile, at
+          // layer 0, and remember it per slot for the later layers of the same tile
+          if (l == 0) {
+            walker_seek(w, t_begin + seq);
+            slot_g[s >> 1] = w.g;
+            slot_base[s >> 1] = w.base;
+          }
+          const int g = slot_g[s >> 1];
+          const long gbase = slot_base[s >> 1];
+          mbar_wait(&mma_done[s], ph_mma[s]);
+          ph_mma[s] ^= 1;
+          tc_fence_after();
+          if (!last) {
+            const float* bias = (l == 0) ? (args.bias1 + ((long)g * NMLP + m) * COUT) : args.bias[m][l];
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+              uint32_t r[16];
+              tmem_ld16(lane_addr + (uint32_t)c0, r);
+              tmem_wait_ld();
+              uint32_t h[8];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * u));
+                const float x0 = fmaxf(__uint_as_float(r[4 * u]) + b4.x, 0.f);
+                const float x1 = fmaxf(__uint_as_float(r[4 * u + 1]) + b4.y, 0.f);
+                const float x2 = fmaxf(__uint_as_float(r[4 * u + 2]) + b4.z, 0.f);
+                const float x3 = fmaxf(__uint_as_float(r[4 * u + 3]) + b4.w, 0.f);
+                h[2 * u] = Elem<T>::pack(x0, x1);
+                h[2 * u + 1] = Elem<T>::pack(x2, x3);
+              }
+              tmem_st8(lane_addr + (uint32_t)COUT + (uint32_t)(c0 / 2), h);
+            }
+            tmem_wait_st();
+          } else {
+            if (g != acc_g || m != acc_m) {
+              flush_stats();
+              acc_g = g;
+              acc_m = m;
+            }
+            const int n = graph_n(args.n_per_graph, g, geo.N);
+            // pixel coordinates with 32-bit arithmetic: one division per tile, then at most two row wraps
+            const int p0 = (int)(t_begin + seq - gbase) * kTileM;
+            int pi = p0 / geo.NPC;
+            int pj = p0 - pi * geo.NPC + pix_in_tile;
+            if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
+            if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
+            const int p = p0 + pix_in_tile;
+            const bool in_plane = pi < geo.N;
+            const bool hole = (pj & (geo.BN - 1)) == geo.BN - 1;
+            const int j = pj - (pj >> geo.BNLOG);
+            const bool valid = in_plane && !hole && pi < n && j < n;
+            // main element and (optionally) the ones row/column element this thread is responsible for
+            long off_main = -1, off_ones = -1;
+            float hole_val = 0.f, ones_val = 0.f;
+            long plane_stride;
+            if (args.out_mode[m] == kOutC) {
+              plane_stride = geo.PSC;
+              if (in_plane) off_main = p;                 // holes are written too (ones or zero)
+              if (hole) hole_val = (args.ones[m] && pi < n) ? 1.f : 0.f;
+            } else {
+              plane_stride = geo.PSA;
+              if (in_plane && !hole && j < geo.N) {
+                const int mt = pi / kTM1;
+                off_main = (long)(pi + mt) * geo.NPA + j;
+                if (args.ones[m] && pi < n && (pi - mt * kTM1 == kTM1 - 1 || pi == n - 1)) {
+                  off_ones = (long)(mt * 128 + 127) * geo.NPA + j;
+                  ones_val = (j < n) ? 1.f : 0.f;
+                }
+              }
+            }
+            T* obase = args.out[m] + (long)g * COUT * plane_stride;
+            T* optr = obase + (off_main >= 0 ? off_main : 0);
+            const bool do_store = off_main >= 0;
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+              uint32_t r[16], qq[16];
+              tmem_ld16(lane_addr + (uint32_t)c0, r);
+              tmem_ld16(q_addr + (uint32_t)c0, qq);
+              tmem_wait_ld();
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const float x = valid ? __uint_as_float(r[u]) : 0.f;
+                acc_s[c0 + u] += x;
+                qq[u] = __float_as_uint(fmaf(x, x, __uint_as_float(qq[u])));
+                r[u] = __float_as_uint(x + hole_val);     // x == 0 in holes: the stored value is the ones/zero marker
+              }
+              tmem_st16(q_addr + (uint32_t)c0, qq);
+              if (do_store) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                  *optr = Elem<T>::from_float(__uint_as_float(r[u]));
+                  optr += plane_stride;
+                }
+              }
+            }
+            if (off_ones >= 0) {                          // rare: last logical row of a 127-row matmul tile
+              T* o1 = obase + off_ones;
+              const T ov = Elem<T>::from_float(ones_val);
+              for (int c = 0; c < COUT; ++c) o1[(long)c * plane_stride] = ov;
+            }
+            tmem_wait_st();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&h_ready[s]);
+        }
       }
     }
+    flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -471,19 +640,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
 
 // =============================================================================================
 // K_B: batched per-(graph, channel) N x N matmul with the GraphNorm rank-1 corrections in the
-// epilogue.  out = a1 a2 (Y1 Y2) + a1 s2 r1 1^T + s1 a2 1 c2^T + s1 s2 n.
-//   A = Y1 plane, K-major (rows i, K = k contiguous); B = Y2 plane, MN-major (rows k, N = j contiguous)
-//   tile 128 x BN, K step 64, kNumStages-deep TMA ring, two TMEM accumulator stages.
+// epilogue.  out = a1 a2 (Y1 Y2) + a1 s2 r1 1^T + s1 a2 1 c2^T + s1 s2 n, r1 / c2 read from the
+// accumulator tile itself (ones column of Y2 / ones row of Y1).
+//   A = Y1 plane (layout A), K-major;  B = Y2 plane (layout C), MN-major;  out = layout C
+//   tile 128 x BN (127 x BN-1 logical), K step 64, kStages-deep TMA ring, two TMEM accumulator stages.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
 // =============================================================================================
 template <typename T>
 struct MatmulArgs {
-  int G, C, N, NP;
-  T* out;                 // [G*C][N][NP]
+  int G, C;
+  Geo geo;
+  T* out;                 // layout C
   const float* coef_a;    // [G*C][2] (a1, s1) or null
   const float* coef_b;    // [G*C][2] (a2, s2) or null
-  const float* r1;        // [G*C][N] row sums of Y1 or null
-  const float* c2;        // [G*C][N] column sums of Y2 or null
   const int32_t* n_per_graph;
 };
 
@@ -499,26 +668,23 @@ struct TileWalker {
   long base = 0;
   int mt = 0, nt = 0;
   long tiles_g = 0;
-  template <int BN>
-  __device__ void init(const int32_t* npg, int N, int C) {
-    g = 0;
-    base = 0;
-    set<BN>(npg, N, C);
-  }
-  template <int BN>
-  __device__ void set(const int32_t* npg, int N, int C) {
+  __device__ void set(const int32_t* npg, int N, int C, int TN1) {
     int n = graph_n(npg, g, N);
-    mt = (n + 127) / 128;
-    nt = (n + BN - 1) / BN;
+    mt = (n + kTM1 - 1) / kTM1;
+    nt = (n + TN1 - 1) / TN1;
     tiles_g = (long)mt * nt * C;
   }
+  __device__ void init(const int32_t* npg, int N, int C, int TN1) {
+    g = 0;
+    base = 0;
+    set(npg, N, C, TN1);
+  }
   // -> plane q, row tile m, col tile nn for flat tile t (t must not decrease between calls)
-  template <int BN>
-  __device__ void locate(long t, const int32_t* npg, int N, int C, int& q, int& m, int& nn, int& n) {
+  __device__ void locate(long t, const int32_t* npg, int N, int C, int TN1, int& q, int& m, int& nn, int& n) {
     while (t >= base + tiles_g) {
       base += tiles_g;
       ++g;
-      set<BN>(npg, N, C);
+      set(npg, N, C, TN1);
     }
     long local = t - base;
     int per_plane = mt * nt;
@@ -548,11 +714,12 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const Geo geo = args.geo;
 
   long total = 0;
   for (int g = 0; g < args.G; ++g) {
-    int n = graph_n(args.n_per_graph, g, args.N);
-    total += (long)((n + 127) / 128) * ((n + BN - 1) / BN) * args.C;
+    int n = graph_n(args.n_per_graph, g, geo.N);
+    total += (long)((n + kTM1 - 1) / kTM1) * ((n + geo.TN1 - 1) / geo.TN1) * args.C;
   }
 
   if (threadIdx.x == 0) {
@@ -572,12 +739,12 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       prefetch_tensormap(&map_a);
       prefetch_tensormap(&map_b);
       TileWalker tw;
-      tw.init<BN>(args.n_per_graph, args.N, args.C);
+      tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
       int stage = 0;
       uint32_t phase = 0;
       for (long t = blockIdx.x; t < total; t += gridDim.x) {
         int q, m, nn, n;
-        tw.locate<BN>(t, args.n_per_graph, args.N, args.C, q, m, nn, n);
+        tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
         const int kts = (n + 63) / 64;
         for (int kt = 0; kt < kts; ++kt) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -596,14 +763,14 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // ================= MMA issuer =================
       const uint32_t idesc = make_idesc(Elem<T>::kFmt, /*A K-major*/ 0, /*B MN-major*/ 1, 128, BN);
       TileWalker tw;
-      tw.init<BN>(args.n_per_graph, args.N, args.C);
+      tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (long t = blockIdx.x; t < total; t += gridDim.x) {
         int q, m, nn, n;
-        tw.locate<BN>(t, args.n_per_graph, args.N, args.C, q, m, nn, n);
+        tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
         const int kts = (n + 63) / 64;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
@@ -629,50 +796,64 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // ================= epilogue (warps 2..5, TMEM lane quadrant = warp % 4) =================
     const int quad = warp % 4;
-    const int et = threadIdx.x - 64;  // 0..127
     TileWalker tw;
-    tw.init<BN>(args.n_per_graph, args.N, args.C);
+    tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
     int as = 0;
     uint32_t aphase = 0;
     for (long t = blockIdx.x; t < total; t += gridDim.x) {
       int q, m, nn, n;
-      tw.locate<BN>(t, args.n_per_graph, args.N, args.C, q, m, nn, n);
+      tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
       float a1 = 1.f, s1 = 0.f, a2 = 1.f, s2 = 0.f;
       if (args.coef_a) { a1 = args.coef_a[2 * q]; s1 = args.coef_a[2 * q + 1]; }
       if (args.coef_b) { a2 = args.coef_b[2 * q]; s2 = args.coef_b[2 * q + 1]; }
-      const int row = m * 128 + quad * 32 + lane;
-      const int j0 = nn * BN;
-      // per-column correction terms for this tile
+      const int r = quad * 32 + lane;        // physical row inside the tile; r == 127 is the ones row
+      const int i = m * kTM1 + r;            // logical row
       float* cc = s_cc + as * BN;
-      for (int col = et; col < BN; col += 128) {
-        int j = j0 + col;
-        cc[col] = (args.c2 && j < n) ? s1 * a2 * args.c2[(long)q * args.N + j] : 0.f;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float scale = a1 * a2;
-      float rc = s1 * s2 * (float)n;
-      if (args.r1 && row < n) rc += a1 * s2 * args.r1[(long)q * args.N + row];
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-      T* orow = args.out + ((long)q * args.N + row) * args.NP + j0;
+      // the warp that owns lane 127 publishes s1*a2*c2[j] for the tile's columns
+      if (quad == 3) {
+        const float k2 = s1 * a2;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t rr[32];
+          tmem_ld32(taddr + (uint32_t)c0, rr);
+          tmem_wait_ld();
+          if (lane == 31) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) cc[c0 + u] = k2 * __uint_as_float(rr[u]);
+          }
+        }
+      }
+      // r1 of this row sits in the tile's last column
+      const float r1 = __uint_as_float(tmem_ld1(taddr + (uint32_t)(BN - 1)));
+      tmem_wait_ld();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float scale = a1 * a2;
+      const float rc = fmaf(a1 * s2, r1, s1 * s2 * (float)n);
+      const bool row_ok = (r < kTM1) && (i < n);
+      T* orow = args.out + (long)q * geo.PSC + (long)i * geo.NPC + (long)nn * BN;
+      const int jlog0 = nn * geo.TN1;        // logical column of tile column 0
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
+        uint32_t rr[32];
+        tmem_ld32(taddr + (uint32_t)c0, rr);
         tmem_wait_ld();
-        if (row < n && j0 + c0 < args.NP) {
+        if (row_ok && jlog0 + c0 < n) {
           uint32_t pk[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            float v0 = fmaf(scale, __uint_as_float(r[2 * u]), rc + cc[c0 + 2 * u]);
-            float v1 = fmaf(scale, __uint_as_float(r[2 * u + 1]), rc + cc[c0 + 2 * u + 1]);
-            pk[u] = Elem<T>::pack(v0, v1);
+            const int ca = c0 + 2 * u, cb = ca + 1;
+            float x0 = fmaf(scale, __uint_as_float(rr[2 * u]), rc + cc[ca]);
+            float x1 = fmaf(scale, __uint_as_float(rr[2 * u + 1]), rc + cc[cb]);
+            if (ca == BN - 1 || jlog0 + ca >= n) x0 = 0.f;   // hole column / beyond the graph: keep zeros
+            if (cb == BN - 1 || jlog0 + cb >= n) x1 = 0.f;
+            pk[u] = Elem<T>::pack(x0, x1);
           }
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
-            if (j0 + c0 + v * 8 < args.NP)  // NP is a multiple of 8: 16-byte vectors never straddle the pitch
-              *reinterpret_cast<uint4*>(orow + c0 + v * 8) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+          for (int vv = 0; vv < 4; ++vv)
+            *reinterpret_cast<uint4*>(orow + c0 + vv * 8) = make_uint4(pk[4 * vv], pk[4 * vv + 1], pk[4 * vv + 2], pk[4 * vv + 3]);
         }
       }
       tc_fence_before();
@@ -747,19 +928,17 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
-
 // ---- launchers -------------------------------------------------------------------------------
 template <typename T>
-int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const float* coef_b, const float* r1,
-                  const float* c2, int G, int C, int N, int NP, const int32_t* npg, cudaStream_t st) {
+int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const float* coef_b, int G, int C,
+                  const Geo& geo, const int32_t* npg, cudaStream_t st) {
   constexpr int is_bf16 = Elem<T>::kFmt;
-  const int BN = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
   CUtensorMap ma, mb;
   const uint64_t planes = (uint64_t)G * C;
-  if (int e = make_map3(&ma, is_bf16, y1, NP, N, planes, NP, (uint64_t)N * NP, 64, 128)) return e;
-  if (int e = make_map3(&mb, is_bf16, y2, NP, N, planes, NP, (uint64_t)N * NP, 64, 64)) return e;
-  MatmulArgs<T> a{G, C, N, NP, out, coef_a, coef_b, r1, c2, npg};
+  // A: columns beyond N are out of bounds (zero filled) so stale pitch padding never reaches the MMA
+  if (int e = make_map3(&ma, is_bf16, y1, geo.N, geo.PRA, planes, geo.NPA, (uint64_t)geo.PSA, 64, 128)) return e;
+  if (int e = make_map3(&mb, is_bf16, y2, geo.NPC, geo.N, planes, geo.NPC, (uint64_t)geo.PSC, 64, 64)) return e;
+  MatmulArgs<T> a{G, C, geo, out, coef_a, coef_b, npg};
   const int grid = num_sms();
 #define FGNN_MM_LAUNCH(BNV)                                                                              \
   do {                                                                                                   \
@@ -772,8 +951,8 @@ int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const f
     tc_matmul_kernel<T, BNV><<<grid, 192, MatmulCfg<BNV>::kSmemBytes, st>>>(ma, mb, a);                   \
   } while (0)
   prof::begin(prof::kMatmul, st);
-  if (BN == 64) FGNN_MM_LAUNCH(64);
-  else if (BN == 128) FGNN_MM_LAUNCH(128);
+  if (geo.BN == 64) FGNN_MM_LAUNCH(64);
+  else if (geo.BN == 128) FGNN_MM_LAUNCH(128);
   else FGNN_MM_LAUNCH(256);
 #undef FGNN_MM_LAUNCH
   prof::end(prof::kMatmul, st);
@@ -786,20 +965,24 @@ struct MlpLaunch {
   const T* src[2];
   int c_src[2];
   int nsrc;
-  const T* w1f;        // [G][COUT][K1g]
-  const float* bias1;  // [G][COUT]
-  const T* wh;         // [depth-1][COUT][Kh]
-  const float* bias[FGNN_MAX_DEPTH];
+  int nmlp;
+  const T* w1f;        // [G][nmlp][COUT][K1g]
+  const float* bias1;  // [G][nmlp][COUT]
+  const T* wh;         // [nmlp][depth-1][COUT][Kh]
+  const float* bias[2][FGNN_MAX_DEPTH];
   int depth, c_out;
-  T* out;
+  T* out[2];
+  int out_mode[2];
+  int ones[2];
+  double* stat_acc;    // [G][nmlp][COUT][2], zeroed here
 };
 
-template <typename T, int COUT>
-int launch_mlp_t(const MlpLaunch<T>& L, int G, int N, int NP, const int32_t* npg, cudaStream_t st) {
+template <typename T, int COUT, int NMLP>
+int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* npg, cudaStream_t st) {
   constexpr int is_bf16 = Elem<T>::kFmt;
-  const long Ppl = (long)N * NP;
   MlpArgs<T> a{};
-  a.G = G; a.N = N; a.NP = NP; a.Ppl = Ppl;
+  a.G = G;
+  a.geo = geo;
   a.nsrc = L.nsrc;
   a.k_src[0] = round_up(L.c_src[0], 16);
   a.k_src[1] = L.nsrc > 1 ? round_up(L.c_src[1], 16) : 0;
@@ -808,54 +991,123 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, int N, int NP, const int32_t* npg
   a.depth = L.depth;
   a.Kh = COUT < 64 ? 64 : COUT;
   a.bias1 = L.bias1;
-  for (int l = 0; l < L.depth; ++l) a.bias[l] = L.bias[l];
-  a.out = L.out;
+  for (int m = 0; m < NMLP; ++m) {
+    for (int l = 0; l < L.depth; ++l) a.bias[m][l] = L.bias[m][l];
+    a.out[m] = L.out[m];
+    a.out_mode[m] = L.out_mode[m];
+    a.ones[m] = L.ones[m];
+  }
+  a.stat_acc = L.stat_acc;
   a.n_per_graph = npg;
   FGNN_CHECK_ARG(a.K1 <= 256, "first-layer K=%d too wide for the tensor-core MLP kernel", a.K1);
   CUtensorMap mx0, mx1, mw1, mwh;
-  if (int e = make_map3(&mx0, is_bf16, L.src[0], Ppl, L.c_src[0], G, Ppl, (uint64_t)L.c_src[0] * Ppl, 64, a.k_src[0])) return e;
+  if (int e = make_map3(&mx0, is_bf16, L.src[0], geo.PSC, L.c_src[0], G, geo.PSC, (uint64_t)L.c_src[0] * geo.PSC, 64, a.k_src[0])) return e;
   if (L.nsrc > 1) {
-    if (int e = make_map3(&mx1, is_bf16, L.src[1], Ppl, L.c_src[1], G, Ppl, (uint64_t)L.c_src[1] * Ppl, 64, a.k_src[1])) return e;
+    if (int e = make_map3(&mx1, is_bf16, L.src[1], geo.PSC, L.c_src[1], G, geo.PSC, (uint64_t)L.c_src[1] * geo.PSC, 64, a.k_src[1])) return e;
   } else {
     mx1 = mx0;
   }
-  if (int e = make_map3(&mw1, is_bf16, L.w1f, a.K1g, COUT, G, a.K1g, (uint64_t)COUT * a.K1g, 64, COUT)) return e;
+  if (int e = make_map3(&mw1, is_bf16, L.w1f, a.K1g, COUT, (uint64_t)G * NMLP, a.K1g, (uint64_t)COUT * a.K1g, 64, COUT)) return e;
   if (L.depth > 1) {
-    if (int e = make_map3(&mwh, is_bf16, L.wh, a.Kh, COUT, L.depth - 1, a.Kh, (uint64_t)COUT * a.Kh, 64, COUT)) return e;
+    if (int e = make_map3(&mwh, is_bf16, L.wh, a.Kh, COUT, (uint64_t)NMLP * (L.depth - 1), a.Kh, (uint64_t)COUT * a.Kh, 64, COUT)) return e;
   } else {
     mwh = mw1;
   }
-  const size_t smem = MlpSmem<COUT>::bytes(a.K1, a.K1g, a.depth, a.Kh);
+  const size_t smem = MlpSmem<COUT, NMLP>::bytes(a.K1, a.K1g, a.depth, a.Kh);
   FGNN_CHECK_ARG(smem <= 227 * 1024, "MLP kernel needs %zu bytes of shared memory", smem);
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
-  const int ctas_per_sm = env_int("FGNN_MLP_CTAS_PER_SM", 2);
-  long total_tiles = (long)G * ((Ppl + kTileM - 1) / kTileM);
-  int grid = (int)std::min<long>((long)num_sms() * ctas_per_sm, total_tiles);
+  FGNN_CUDA(cudaMemsetAsync(L.stat_acc, 0, (size_t)G * NMLP * COUT * 2 * sizeof(double), st));
+  long total_tiles = (long)G * ((geo.PSC + kTileM - 1) / kTileM);
+  int grid = (int)std::min<long>((long)num_sms(), total_tiles);
   if (grid < 1) grid = 1;
   prof::begin(prof::kMlp, st);
-  tc_mlp_kernel<T, COUT><<<grid, 160, smem, st>>>(mx0, mx1, mw1, mwh, a);
+  tc_mlp_kernel<T, COUT, NMLP><<<grid, 320, smem, st>>>(mx0, mx1, mw1, mwh, a);
   prof::end(prof::kMlp, st);
   FGNN_LAUNCHED();
   return FGNN_OK;
 }
 
 template <typename T>
-int launch_mlp(const MlpLaunch<T>& L, int G, int N, int NP, const int32_t* npg, cudaStream_t st) {
-  if (L.c_out == 32) return launch_mlp_t<T, 32>(L, G, N, NP, npg, st);
-  if (L.c_out == 64) return launch_mlp_t<T, 64>(L, G, N, NP, npg, st);
+int launch_mlp(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* npg, cudaStream_t st) {
+  if (L.c_out == 32 && L.nmlp == 1) return launch_mlp_t<T, 32, 1>(L, G, geo, npg, st);
+  if (L.c_out == 32 && L.nmlp == 2) return launch_mlp_t<T, 32, 2>(L, G, geo, npg, st);
+  if (L.c_out == 64 && L.nmlp == 1) return launch_mlp_t<T, 64, 1>(L, G, geo, npg, st);
+  if (L.c_out == 64 && L.nmlp == 2) return launch_mlp_t<T, 64, 2>(L, G, geo, npg, st);
   return fail(FGNN_ERR_UNSUPPORTED, "tensor-core path supports out_features 32 or 64 (got %d); use FGNN_FP32", L.c_out);
 }
 
+// fold + conv chain(s) + statistics finalisation for 1 or 2 MLPs sharing their input
 template <typename T>
-int launch_stats(const T* y, const float* gw, const float* gb, float eps, float* coef, float* rsum, float* csum,
-                 int G, int C, int N, int NP, const int32_t* npg, cudaStream_t st) {
+struct MlpGroup {
+  int nmlp;
+  const fgnn_mlp_params* mp[2];
+  const T* src[2];
+  int c_src[2];
+  const float* src_coef[2];
+  int nsrc;
+  T* wf;
+  float* bf;
+  const T* wh;       // [nmlp][depth-1][C][Kh]
+  T* out[2];
+  int out_mode[2];
+  int ones[2];
+  float* coef[2];
+  double* stat_acc;
+};
+
+template <typename T>
+int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int32_t* npg, cudaStream_t st) {
+  FoldArgs fa{};
+  fa.nmlp = M.nmlp;
+  fa.nsrc = M.nsrc;
+  for (int m = 0; m < M.nmlp; ++m) { fa.w[m] = M.mp[m]->w[0]; fa.b[m] = M.mp[m]->b[0]; }
+  fa.c[0] = M.c_src[0];
+  fa.c[1] = M.nsrc > 1 ? M.c_src[1] : 0;
+  fa.coef[0] = M.src_coef[0];
+  fa.coef[1] = M.nsrc > 1 ? M.src_coef[1] : nullptr;
+  fa.koff[0] = 0;
+  fa.koff[1] = round_up(M.c_src[0], 16);
+  fa.c_out = C;
+  fa.K1g = round_up(round_up(M.c_src[0], 16) + (M.nsrc > 1 ? round_up(M.c_src[1], 16) : 0), 64);
+  fold_weights_kernel<T><<<G, 256, 0, st>>>(fa, M.wf, M.bf);
+  FGNN_LAUNCHED();
+  MlpLaunch<T> L{};
+  L.nmlp = M.nmlp;
+  L.nsrc = M.nsrc;
+  for (int s = 0; s < 2; ++s) { L.src[s] = M.src[s]; L.c_src[s] = M.c_src[s]; }
+  L.w1f = M.wf;
+  L.bias1 = M.bf;
+  L.wh = M.wh;
+  L.depth = M.mp[0]->depth;
+  L.c_out = C;
+  for (int m = 0; m < M.nmlp; ++m) {
+    FGNN_CHECK_ARG(M.mp[m]->depth == L.depth, "MLPs fused in one launch must have the same depth");
+    for (int l = 0; l < L.depth; ++l) L.bias[m][l] = M.mp[m]->b[l];
+    L.out[m] = M.out[m];
+    L.out_mode[m] = M.out_mode[m];
+    L.ones[m] = M.ones[m];
+  }
+  L.stat_acc = M.stat_acc;
+  if (int e = launch_mlp<T>(L, G, geo, npg, st)) return e;
+  CoefArgs ca{};
+  ca.acc = M.stat_acc;
+  ca.nmlp = M.nmlp;
+  ca.C = C;
+  ca.N = geo.N;
+  ca.n_per_graph = npg;
+  for (int m = 0; m < M.nmlp; ++m) {
+    ca.coef[m] = M.coef[m];
+    ca.gw[m] = M.mp[m]->gn_w;
+    ca.gb[m] = M.mp[m]->gn_b;
+    ca.eps[m] = M.mp[m]->eps;
+  }
+  const int total = G * M.nmlp * C;
   prof::begin(prof::kStats, st);
-  plane_stats16_kernel<T><<<G * C, 256, (size_t)8 * NP * sizeof(float), st>>>(y, gw, gb, eps, coef, rsum, csum, C, N,
-                                                                              NP, npg);
+  finalize_coef_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ca, total);
   prof::end(prof::kStats, st);
   FGNN_LAUNCHED();
   return FGNN_OK;
@@ -863,15 +1115,14 @@ int launch_stats(const T* y, const float* gw, const float* gb, float eps, float*
 
 // ---- workspace plan -----------------------------------------------------------------------------
 struct Plan {
-  int chunk, C, cin0, N, NP, depth_max;
-  long Ppl;
+  int chunk, C, cin0, depth_max;
+  Geo geo;
   int K1g12_max, K1g3_max;
 };
 
 int make_plan(const fgnn_embed_params& p, int G, int N, Plan& pl) {
-  pl.N = N;
-  pl.NP = round_up(N, 8);
-  pl.Ppl = (long)N * pl.NP;
+  if (N > kMaxN) return fail(FGNN_ERR_UNSUPPORTED, "tensor-core path supports N <= %d (got %d)", kMaxN, N);
+  pl.geo = make_geo(N);
   pl.C = p.block[0].mlp1.c_out;
   pl.cin0 = p.block[0].mlp1.c_in;
   pl.depth_max = 1;
@@ -884,6 +1135,8 @@ int make_plan(const fgnn_embed_params& p, int G, int N, Plan& pl) {
       return fail(FGNN_ERR_UNSUPPORTED, "tensor-core path needs in_features == out_features for every block");
     if (bp.mlp1.c_in != cur || bp.mlp2.c_in != cur || bp.mlp3.c_in != cur + pl.C)
       return fail(FGNN_ERR_INVALID, "block %d: channel counts do not chain", b);
+    if (bp.mlp1.depth != bp.mlp2.depth)
+      return fail(FGNN_ERR_UNSUPPORTED, "block %d: mlp1 and mlp2 must have the same depth", b);
     pl.depth_max = std::max(pl.depth_max, std::max(bp.mlp1.depth, std::max(bp.mlp2.depth, bp.mlp3.depth)));
     pl.K1g12_max = std::max(pl.K1g12_max, round_up(round_up(cur, 16), 64));
     pl.K1g3_max = std::max(pl.K1g3_max, round_up(pl.C + round_up(cur, 16), 64));
@@ -891,10 +1144,9 @@ int make_plan(const fgnn_embed_params& p, int G, int N, Plan& pl) {
   }
   if (pl.C != 32 && pl.C != 64)
     return fail(FGNN_ERR_UNSUPPORTED, "tensor-core path supports in/out_features 32 or 64 (got %d); use FGNN_FP32", pl.C);
-  if (N > kMaxN) return fail(FGNN_ERR_UNSUPPORTED, "tensor-core path supports N <= %d (got %d)", kMaxN, N);
   if (pl.cin0 > 64) return fail(FGNN_ERR_UNSUPPORTED, "original_features_num %d > 64 unsupported", pl.cin0);
   const int chunk_env = env_int("FGNN_TC_CHUNK", 0);
-  long per_graph = (long)(5 * pl.C + pl.cin0) * pl.Ppl * 2;
+  long per_graph = ((long)(4 * pl.C + pl.cin0) * pl.geo.PSC + (long)pl.C * pl.geo.PSA) * 2;
   long budget = (long)6 << 30;
   long chunk = chunk_env > 0 ? chunk_env : std::max<long>(1, budget / std::max<long>(per_graph, 1));
   chunk = std::min<long>(chunk, 65535 / std::max(pl.C, pl.cin0));   // grid.y limits of the helper kernels
@@ -905,34 +1157,30 @@ int make_plan(const fgnn_embed_params& p, int G, int N, Plan& pl) {
 struct Buffers {
   void *xin, *xa, *xb, *y1, *y2, *mult;        // 16-bit planes
   float *coef1, *coef2, *coef3a, *coef3b;      // [chunk][C][2]
-  float *r1, *c2, *scratch_rc;                 // [chunk][C][N]
-  void *wf1, *wf2, *wf3;                       // folded first-layer weights
-  float *bf1, *bf2, *bf3;                      // folded first-layer biases
+  void *wf12, *wf3;                            // folded first-layer weights
+  float *bf12, *bf3;                           // folded first-layer biases
+  double* stat_acc;                            // [chunk][2][C][2]
   void* wh;                                    // [blocks][3][depth-1][C][Kh]
 };
 
 size_t carve(const Plan& pl, int num_blocks, Arena& ar, Buffers& B) {
-  const size_t act = (size_t)pl.chunk * pl.C * pl.Ppl;
-  B.xin = ar.take<uint16_t>((size_t)pl.chunk * pl.cin0 * pl.Ppl, 1024);
-  B.xa = ar.take<uint16_t>(act, 1024);
-  B.xb = ar.take<uint16_t>(act, 1024);
-  B.y1 = ar.take<uint16_t>(act, 1024);
-  B.y2 = ar.take<uint16_t>(act, 1024);
-  B.mult = ar.take<uint16_t>(act, 1024);
+  const size_t actC = (size_t)pl.chunk * pl.C * pl.geo.PSC;
+  B.xin = ar.take<uint16_t>((size_t)pl.chunk * pl.cin0 * pl.geo.PSC, 1024);
+  B.xa = ar.take<uint16_t>(actC, 1024);
+  B.xb = ar.take<uint16_t>(actC, 1024);
+  B.y1 = ar.take<uint16_t>((size_t)pl.chunk * pl.C * pl.geo.PSA, 1024);
+  B.y2 = ar.take<uint16_t>(actC, 1024);
+  B.mult = ar.take<uint16_t>(actC, 1024);
   const size_t nc = (size_t)pl.chunk * pl.C;
   B.coef1 = ar.take<float>(nc * 2);
   B.coef2 = ar.take<float>(nc * 2);
   B.coef3a = ar.take<float>(nc * 2);
   B.coef3b = ar.take<float>(nc * 2);
-  B.r1 = ar.take<float>(nc * pl.N);
-  B.c2 = ar.take<float>(nc * pl.N);
-  B.scratch_rc = ar.take<float>(nc * pl.N);
-  B.wf1 = ar.take<uint16_t>(nc * pl.K1g12_max, 1024);
-  B.wf2 = ar.take<uint16_t>(nc * pl.K1g12_max, 1024);
+  B.wf12 = ar.take<uint16_t>(2 * nc * pl.K1g12_max, 1024);
   B.wf3 = ar.take<uint16_t>(nc * pl.K1g3_max, 1024);
-  B.bf1 = ar.take<float>(nc);
-  B.bf2 = ar.take<float>(nc);
+  B.bf12 = ar.take<float>(2 * nc);
   B.bf3 = ar.take<float>(nc);
+  B.stat_acc = ar.take<double>(4 * nc);
   const int Kh = pl.C < 64 ? 64 : pl.C;
   B.wh = ar.take<uint16_t>((size_t)num_blocks * 3 * std::max(pl.depth_max - 1, 1) * pl.C * Kh, 1024);
   return align_up(ar.off, 1024);
@@ -947,52 +1195,30 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, i
   Buffers B;
   size_t need = carve(pl, p.num_blocks, ar, B);
   if (need > ws_bytes) return fail(FGNN_ERR_WORKSPACE, "embed workspace too small: %zu < %zu", ws_bytes, need);
-  const int C = pl.C, NP = pl.NP;
+  const int C = pl.C;
+  const Geo& geo = pl.geo;
   const int Kh = C < 64 ? 64 : C;
   const int dm1 = std::max(pl.depth_max - 1, 1);
-  // hidden-layer weights -> 16-bit, once per call
+  // hidden-layer weights -> 16-bit, once per call.  Layout [block][3 * dm1 matrices][C][Kh]: mlp1's and
+  // mlp2's matrices are packed back to back (one tensor map serves the fused launch), mlp3's start at 2*dm1.
   for (int b = 0; b < p.num_blocks; ++b) {
     const fgnn_mlp_params* mlps[3] = {&p.block[b].mlp1, &p.block[b].mlp2, &p.block[b].mlp3};
     for (int j = 0; j < 3; ++j)
       for (int l = 1; l < mlps[j]->depth; ++l) {
-        T* dst = reinterpret_cast<T*>(B.wh) + (((size_t)b * 3 + j) * dm1 + (l - 1)) * C * Kh;
+        const int dj = mlps[j]->depth - 1;
+        T* dst = reinterpret_cast<T*>(B.wh) +
+                 ((size_t)b * 3 * dm1 + (size_t)(j < 2 ? j * dj : 2 * dm1) + (l - 1)) * C * Kh;
         convert_weight_kernel<T><<<ceil_div(C * Kh, 256), 256, 0, st>>>(mlps[j]->w[l], dst, C, C, Kh);
         FGNN_LAUNCHED();
       }
   }
-  auto run_mlp = [&](const fgnn_mlp_params& mp, int bidx, int j, const T* s0, int c0, const float* coef0, const T* s1,
-                     int c1, const float* coef1, T* wf, float* bf, T* out, int gc, const int32_t* n_c) -> int {
-    FoldArgs fa{};
-    fa.w = mp.w[0];
-    fa.b = mp.b[0];
-    fa.nsrc = s1 ? 2 : 1;
-    fa.c[0] = c0; fa.c[1] = c1;
-    fa.coef[0] = coef0; fa.coef[1] = coef1;
-    fa.koff[0] = 0; fa.koff[1] = round_up(c0, 16);
-    fa.c_out = C;
-    fa.K1g = round_up(round_up(c0, 16) + (s1 ? round_up(c1, 16) : 0), 64);
-    fold_weights_kernel<T><<<gc, 256, 0, st>>>(fa, wf, bf);
-    FGNN_LAUNCHED();
-    MlpLaunch<T> L{};
-    L.src[0] = s0; L.src[1] = s1;
-    L.c_src[0] = c0; L.c_src[1] = c1;
-    L.nsrc = fa.nsrc;
-    L.w1f = wf;
-    L.bias1 = bf;
-    L.wh = reinterpret_cast<const T*>(B.wh) + ((size_t)bidx * 3 + j) * dm1 * C * Kh;
-    for (int l = 0; l < mp.depth; ++l) L.bias[l] = mp.b[l];
-    L.depth = mp.depth;
-    L.c_out = C;
-    L.out = out;
-    return launch_mlp<T>(L, gc, N, NP, n_c, st);
-  };
   for (int g0 = 0; g0 < G; g0 += pl.chunk) {
     const int gc = std::min(pl.chunk, G - g0);
     const int32_t* n_c = npg ? npg + g0 : nullptr;
     {
-      dim3 grid((unsigned)std::min<long>(64, (pl.Ppl + 255) / 256), gc * pl.cin0);
+      dim3 grid((unsigned)std::min<long>(64, (geo.PSC + 255) / 256), gc * pl.cin0);
       to_planes_kernel<T><<<grid, 256, 0, st>>>(x + (size_t)g0 * pl.cin0 * N * N, reinterpret_cast<T*>(B.xin), pl.cin0,
-                                                N, NP, n_c);
+                                                geo, 0, n_c);
       FGNN_LAUNCHED();
     }
     const T* cur = reinterpret_cast<const T*>(B.xin);
@@ -1005,16 +1231,32 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, i
     T* mult = reinterpret_cast<T*>(B.mult);
     for (int b = 0; b < p.num_blocks; ++b) {
       const fgnn_block_params& bp = p.block[b];
-      if (int e = run_mlp(bp.mlp1, b, 0, cur, cur_c, cur_coef, nullptr, 0, nullptr, reinterpret_cast<T*>(B.wf1), B.bf1,
-                          y1, gc, n_c)) return e;
-      if (int e = run_mlp(bp.mlp2, b, 1, cur, cur_c, cur_coef, nullptr, 0, nullptr, reinterpret_cast<T*>(B.wf2), B.bf2,
-                          y2, gc, n_c)) return e;
-      if (int e = launch_stats<T>(y1, bp.mlp1.gn_w, bp.mlp1.gn_b, bp.mlp1.eps, B.coef1, B.r1, nullptr, gc, C, N, NP, n_c, st)) return e;
-      if (int e = launch_stats<T>(y2, bp.mlp2.gn_w, bp.mlp2.gn_b, bp.mlp2.eps, B.coef2, nullptr, B.c2, gc, C, N, NP, n_c, st)) return e;
-      if (int e = launch_matmul<T>(y1, y2, mult, B.coef1, B.coef2, B.r1, B.c2, gc, C, N, NP, n_c, st)) return e;
-      if (int e = run_mlp(bp.mlp3, b, 2, mult, C, nullptr, cur, cur_c, cur_coef, reinterpret_cast<T*>(B.wf3), B.bf3, nxt,
-                          gc, n_c)) return e;
-      if (int e = launch_stats<T>(nxt, bp.mlp3.gn_w, bp.mlp3.gn_b, bp.mlp3.eps, nxt_coef, nullptr, nullptr, gc, C, N, NP, n_c, st)) return e;
+      const T* whb = reinterpret_cast<const T*>(B.wh) + (size_t)b * 3 * dm1 * C * Kh;
+      {
+        MlpGroup<T> M{};
+        M.nmlp = 2;
+        M.mp[0] = &bp.mlp1; M.mp[1] = &bp.mlp2;
+        M.src[0] = cur; M.c_src[0] = cur_c; M.src_coef[0] = cur_coef; M.nsrc = 1;
+        M.wf = reinterpret_cast<T*>(B.wf12); M.bf = B.bf12;
+        M.wh = whb;
+        M.out[0] = y1; M.out_mode[0] = kOutA; M.ones[0] = 1; M.coef[0] = B.coef1;
+        M.out[1] = y2; M.out_mode[1] = kOutC; M.ones[1] = 1; M.coef[1] = B.coef2;
+        M.stat_acc = B.stat_acc;
+        if (int e = run_mlp_group<T>(M, C, gc, geo, n_c, st)) return e;
+      }
+      if (int e = launch_matmul<T>(y1, y2, mult, B.coef1, B.coef2, gc, C, geo, n_c, st)) return e;
+      {
+        MlpGroup<T> M{};
+        M.nmlp = 1;
+        M.mp[0] = &bp.mlp3;
+        M.src[0] = mult; M.c_src[0] = C; M.src_coef[0] = nullptr;
+        M.src[1] = cur; M.c_src[1] = cur_c; M.src_coef[1] = cur_coef; M.nsrc = 2;
+        M.wf = reinterpret_cast<T*>(B.wf3); M.bf = B.bf3;
+        M.wh = whb + (size_t)2 * dm1 * C * Kh;
+        M.out[0] = nxt; M.out_mode[0] = kOutC; M.ones[0] = 0; M.coef[0] = nxt_coef;
+        M.stat_acc = B.stat_acc;
+        if (int e = run_mlp_group<T>(M, C, gc, geo, n_c, st)) return e;
+      }
       cur = nxt;
       cur_c = C;
       cur_coef = nxt_coef;
@@ -1022,7 +1264,7 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, i
       nxt_coef = (nxt_coef == B.coef3a) ? B.coef3b : B.coef3a;
     }
     const long rows = (long)gc * C * N;
-    pool_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cur, cur_coef, emb + (size_t)g0 * C * N, C, N, NP, rows, n_c);
+    pool_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cur, cur_coef, emb + (size_t)g0 * C * N, C, geo, rows, n_c);
     FGNN_LAUNCHED();
   }
   return FGNN_OK;
@@ -1050,28 +1292,28 @@ int embed_fwd(const fgnn_embed_params& p, int precision, const float* x, float* 
 
 // ---- debug: one tensor-core matmul on fp32 host-layout tensors ---------------------------------
 size_t debug_matmul_workspace_bytes(int G, int C, int N) {
-  const int NP = round_up(N, 8);
-  return align_up((size_t)3 * G * C * N * NP * 2 + 4096, 1024);
+  Geo geo = make_geo(N);
+  return align_up(((size_t)2 * G * C * geo.PSC + (size_t)G * C * geo.PSA) * 2 + 8192, 1024);
 }
 
 template <typename T>
 int debug_matmul_t(const float* a, const float* b, float* out, int G, int C, int N, const int32_t* npg, void* ws,
                    size_t ws_bytes, cudaStream_t st) {
-  const int NP = round_up(N, 8);
-  const size_t act = (size_t)G * C * N * NP;
+  Geo geo = make_geo(N);
   if (ws_bytes < debug_matmul_workspace_bytes(G, C, N)) return fail(FGNN_ERR_WORKSPACE, "debug workspace too small");
   Arena ar(ws, ws_bytes);
-  T* y1 = ar.take<T>(act, 1024);
-  T* y2 = ar.take<T>(act, 1024);
-  T* mo = ar.take<T>(act, 1024);
-  const long Ppl = (long)N * NP;
-  dim3 grid((unsigned)std::min<long>(64, (Ppl + 255) / 256), G * C);
-  to_planes_kernel<T><<<grid, 256, 0, st>>>(a, y1, C, N, NP, npg);
+  T* y1 = ar.take<T>((size_t)G * C * geo.PSA, 1024);
+  T* y2 = ar.take<T>((size_t)G * C * geo.PSC, 1024);
+  T* mo = ar.take<T>((size_t)G * C * geo.PSC, 1024);
+  dim3 gridA((unsigned)std::min<long>(64, (geo.PSA + 255) / 256), G * C);
+  dim3 gridC((unsigned)std::min<long>(64, (geo.PSC + 255) / 256), G * C);
+  to_planes_kernel<T><<<gridA, 256, 0, st>>>(a, y1, C, geo, 1, npg);
   FGNN_LAUNCHED();
-  to_planes_kernel<T><<<grid, 256, 0, st>>>(b, y2, C, N, NP, npg);
+  to_planes_kernel<T><<<gridC, 256, 0, st>>>(b, y2, C, geo, 0, npg);
   FGNN_LAUNCHED();
-  if (int e = launch_matmul<T>(y1, y2, mo, nullptr, nullptr, nullptr, nullptr, G, C, N, NP, npg, st)) return e;
-  from_planes_kernel<T><<<grid, 256, 0, st>>>(mo, out, nullptr, C, N, NP, npg);
+  FGNN_CUDA(cudaMemsetAsync(mo, 0, (size_t)G * C * geo.PSC * sizeof(T), st));
+  if (int e = launch_matmul<T>(y1, y2, mo, nullptr, nullptr, G, C, geo, npg, st)) return e;
+  from_planes_kernel<T><<<gridC, 256, 0, st>>>(mo, out, nullptr, C, geo, npg);
   FGNN_LAUNCHED();
   return FGNN_OK;
 }
@@ -1086,54 +1328,51 @@ int debug_matmul(int precision, const float* a, const float* b, float* out, int 
   return fail(FGNN_ERR_INVALID, "precision must be FGNN_BF16 or FGNN_FP16");
 }
 
-// ---- debug: one tensor-core MlpBlock_Real (fold -> conv chain -> stats -> normalise) ----------------
+// ---- debug: one tensor-core MlpBlock_Real (fold -> conv chain + statistics -> normalise) ----------
 size_t debug_mlp_workspace_bytes(int G, int c_in, int c_out, int depth, int N) {
-  const int NP = round_up(N, 8);
-  const size_t Ppl = (size_t)N * NP;
+  Geo geo = make_geo(N);
   const int K1g = round_up(round_up(c_in, 16), 64);
   const int Kh = c_out < 64 ? 64 : c_out;
-  return align_up((size_t)G * (c_in + c_out) * Ppl * 2 + (size_t)G * c_out * K1g * 2 +
-                      (size_t)std::max(depth - 1, 1) * c_out * Kh * 2 + (size_t)G * c_out * 3 * 4 + 16384, 1024);
+  return align_up((size_t)G * (c_in + c_out) * geo.PSC * 2 + (size_t)G * c_out * K1g * 2 +
+                      (size_t)std::max(depth - 1, 1) * c_out * Kh * 2 + (size_t)G * c_out * (3 * 4 + 16) + 16384, 1024);
 }
 
 template <typename T>
 int debug_mlp_t(const fgnn_mlp_params& mp, const float* x, float* y, int G, int N, const int32_t* npg, void* ws,
                 size_t ws_bytes, cudaStream_t st) {
-  const int NP = round_up(N, 8);
-  const size_t Ppl = (size_t)N * NP;
+  Geo geo = make_geo(N);
   const int C = mp.c_out;
   const int K1g = round_up(round_up(mp.c_in, 16), 64);
   const int Kh = C < 64 ? 64 : C;
   if (ws_bytes < debug_mlp_workspace_bytes(G, mp.c_in, C, mp.depth, N)) return fail(FGNN_ERR_WORKSPACE, "debug workspace too small");
   FGNN_CHECK_ARG(mp.c_in <= 128, "c_in too large for the debug entry");
   Arena ar(ws, ws_bytes);
-  T* xin = ar.take<T>((size_t)G * mp.c_in * Ppl, 1024);
-  T* out = ar.take<T>((size_t)G * C * Ppl, 1024);
+  T* xin = ar.take<T>((size_t)G * mp.c_in * geo.PSC, 1024);
+  T* out = ar.take<T>((size_t)G * C * geo.PSC, 1024);
   T* wf = ar.take<T>((size_t)G * C * K1g, 1024);
   T* wh = ar.take<T>((size_t)std::max(mp.depth - 1, 1) * C * Kh, 1024);
   float* bf = ar.take<float>((size_t)G * C);
   float* coef = ar.take<float>((size_t)G * C * 2);
+  double* acc = ar.take<double>((size_t)G * C * 2);
   {
-    dim3 grid((unsigned)std::min<size_t>(64, (Ppl + 255) / 256), G * mp.c_in);
-    to_planes_kernel<T><<<grid, 256, 0, st>>>(x, xin, mp.c_in, N, NP, npg);
+    dim3 grid((unsigned)std::min<long>(64, (geo.PSC + 255) / 256), G * mp.c_in);
+    to_planes_kernel<T><<<grid, 256, 0, st>>>(x, xin, mp.c_in, geo, 0, npg);
     FGNN_LAUNCHED();
   }
   for (int l = 1; l < mp.depth; ++l) {
     convert_weight_kernel<T><<<ceil_div(C * Kh, 256), 256, 0, st>>>(mp.w[l], wh + (size_t)(l - 1) * C * Kh, C, C, Kh);
     FGNN_LAUNCHED();
   }
-  FoldArgs fa{};
-  fa.w = mp.w[0]; fa.b = mp.b[0]; fa.nsrc = 1; fa.c[0] = mp.c_in; fa.koff[0] = 0; fa.c_out = C; fa.K1g = K1g;
-  fold_weights_kernel<T><<<G, 256, 0, st>>>(fa, wf, bf);
-  FGNN_LAUNCHED();
-  MlpLaunch<T> L{};
-  L.src[0] = xin; L.c_src[0] = mp.c_in; L.nsrc = 1; L.w1f = wf; L.bias1 = bf; L.wh = wh;
-  for (int l = 0; l < mp.depth; ++l) L.bias[l] = mp.b[l];
-  L.depth = mp.depth; L.c_out = C; L.out = out;
-  if (int e = launch_mlp<T>(L, G, N, NP, npg, st)) return e;
-  if (int e = launch_stats<T>(out, mp.gn_w, mp.gn_b, mp.eps, coef, nullptr, nullptr, G, C, N, NP, npg, st)) return e;
-  dim3 grid((unsigned)std::min<size_t>(64, (Ppl + 255) / 256), G * C);
-  from_planes_kernel<T><<<grid, 256, 0, st>>>(out, y, coef, C, N, NP, npg);
+  MlpGroup<T> M{};
+  M.nmlp = 1;
+  M.mp[0] = &mp;
+  M.src[0] = xin; M.c_src[0] = mp.c_in; M.src_coef[0] = nullptr; M.nsrc = 1;
+  M.wf = wf; M.bf = bf; M.wh = wh;
+  M.out[0] = out; M.out_mode[0] = kOutC; M.ones[0] = 0; M.coef[0] = coef;
+  M.stat_acc = acc;
+  if (int e = run_mlp_group<T>(M, C, G, geo, npg, st)) return e;
+  dim3 grid((unsigned)std::min<long>(64, (geo.PSC + 255) / 256), G * C);
+  from_planes_kernel<T><<<grid, 256, 0, st>>>(out, y, coef, C, geo, npg);
   FGNN_LAUNCHED();
   return FGNN_OK;
 }
@@ -1143,6 +1382,7 @@ int debug_mlp(int precision, const fgnn_mlp_params& mp, const float* x, float* y
   if (!fgnn_device_supports_tcgen05()) return fail(FGNN_ERR_UNSUPPORTED, "needs an sm_100 device");
   FGNN_CHECK_ARG(x && y && ws, "null pointer");
   FGNN_CHECK_ARG(N <= kMaxN, "N too large");
+  if (mp.c_out != 32 && mp.c_out != 64) return fail(FGNN_ERR_UNSUPPORTED, "c_out must be 32 or 64");
   if (precision == FGNN_BF16) return debug_mlp_t<__nv_bfloat16>(mp, x, y, G, N, n_per_graph, ws, ws_bytes, st);
   if (precision == FGNN_FP16) return debug_mlp_t<__half>(mp, x, y, G, N, n_per_graph, ws, ws_bytes, st);
   return fail(FGNN_ERR_INVALID, "precision must be FGNN_BF16 or FGNN_FP16");

@@ -120,7 +120,9 @@ def check_embed(n, c, pairs, sizes=None, reg=False):
         et = e.tensor.rename(None).cpu()
         worst = max(rel(et[i, :, :s], refs[i]) for i, s in enumerate(sizes))
         pad = max(float(et[i, :, s:].abs().sum()) for i, s in enumerate(sizes))
-        print(f"embed[{prec_name}] ragged {sizes} c={c}: worst rel err {worst:.3e}, padding abs sum {pad}")
+        print(f"embed[{prec_name}] ragged {sizes} c={c}: worst rel err {worst:.3e}, padding abs sum {pad}; per graph",
+              [f"{rel(et[i, :, :s], refs[i]):.2e}" for i, s in enumerate(sizes)],
+              "finite", [bool(torch.isfinite(et[i]).all()) for i in range(len(sizes))])
 
 
 if stage == "matmul64":
@@ -148,6 +150,12 @@ elif stage == "embed":
 elif stage == "embed_ragged":
     check_embed(0, 32, 0, sizes=[50, 23, 37, 64])
     check_embed(0, 64, 0, sizes=[130, 70])
+elif stage == "ragged_probe":
+    for sizes in ([130], [130, 130], [70, 130], [130, 70], [100, 70], [200, 150], [129, 128], [140, 127]):
+        try:
+            check_embed(0, 64, 0, sizes=sizes)
+        except Exception as ex:
+            print("FAILED", sizes, ex)
 else:
     raise SystemExit("unknown stage")
 print("STAGE", stage, prec_name, "OK")
