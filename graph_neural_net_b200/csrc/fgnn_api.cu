@@ -273,6 +273,8 @@ int fgnn_debug_tc_mlp(int32_t precision, const fgnn_mlp_params* p, const float* 
   return tc::debug_mlp(precision, *p, x, y, G, N, n_per_graph, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+void fgnn_debug_dump_timing(void) { tc::dump_timing(); }
+
 void fgnn_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(prof::g_mu);
   prof::g_enabled = on != 0;

@@ -241,7 +241,7 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ c
 //   layer>=2: D = relu(D + b) (16-bit, written back to TMEM) * W^T        A = TMEM, B = smem
 //   output: raw last-layer accumulators as 16-bit planes (the last bias cancels in GraphNorm), their
 //           per-(graph, channel) sum and sum of squares (fp32 in registers, double atomics per flush).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups that
+// Warp roles: warps 0-3 / 4-7 two epilogue groups, warp 8 TMA producer, warp 9 MMA issuer; the groups
 // alternate virtual tiles (slot parity).  TMEM slot s: accumulator columns [s*1.5*COUT, +COUT),
 // packed hidden activations in the next COUT/2 columns.
 // =============================================================================================
@@ -263,6 +263,18 @@ struct MlpArgs {
 };
 
 constexpr int kSlots = 4;
+
+// Optional cycle accounting of the conv-chain kernel's roles (compile with -DFGNN_TC_TIMING; bring-up only).
+#ifdef FGNN_TC_TIMING
+__device__ unsigned long long g_tc_timing[16];
+#define TIMING_DECL long long tm_t0 = clock64(), tm_acc[6] = {0, 0, 0, 0, 0, 0}
+#define TIMING_MARK(slot) do { long long tm_t1 = clock64(); tm_acc[slot] += tm_t1 - tm_t0; tm_t0 = tm_t1; } while (0)
+#define TIMING_FLUSH(base, cond) do { if (cond) for (int tm_i = 0; tm_i < 6; ++tm_i) atomicAdd(&g_tc_timing[(base) + tm_i], (unsigned long long)tm_acc[tm_i]); } while (0)
+#else
+#define TIMING_DECL
+#define TIMING_MARK(slot)
+#define TIMING_FLUSH(base, cond)
+#endif
 constexpr int kInStages = 4;
 
 template <int COUT, int NMLP>
@@ -303,7 +315,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   uint64_t* h_ready = mma_done + kSlots;      // [kSlots]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + kSlots);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
 
   // ---- tile range of this CTA: contiguous chunk of the flat (graph, tile) list ----------------
   long total = 0;
@@ -319,7 +331,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&h_ready[s], 4); }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -344,125 +356,148 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   };
 
 
-  if (warp == 0) {
-    if (lane == 0 && V > 0) {
-      // ================= TMA producer =================
-      prefetch_tensormap(&map_x0);
-      prefetch_tensormap(&map_w1);
+  // Warp ids: the scheduler favours higher warp ids, and the two control warps must never be starved by
+  // epilogue warps polling an mbarrier on the same sub-partition -> control warps get the highest ids.
+  if (warp == 8) {
+    if (V > 0) {
+      // ================= TMA producer (whole warp, elected lane issues) =================
+      if (lane == 0) {
+        prefetch_tensormap(&map_x0);
+        prefetch_tensormap(&map_w1);
+      }
       if (depth > 1) {
         const int atoms = Kh / 64;
-        mbar_arrive_expect_tx(wh_full, (uint32_t)(NMLP * (depth - 1)) * wh_mat_bytes);
+        mbar_arrive_expect_tx_e(wh_full, (uint32_t)(NMLP * (depth - 1)) * wh_mat_bytes);
         for (int m = 0; m < NMLP; ++m)
           for (int l = 0; l < depth - 1; ++l)
             for (int at = 0; at < atoms; ++at)
-              tma_load_3d(s_wh + ((size_t)(m * (depth - 1) + l) * atoms + at) * COUT * 128, &map_wh, wh_full, at * 64,
+              tma_load_3d_e(s_wh + ((size_t)(m * (depth - 1) + l) * atoms + at) * COUT * 128, &map_wh, wh_full, at * 64,
                           0, m * (depth - 1) + l);
       }
       Walker w;
       walker_init(w);
       int cur_g = -1, nchg = 0;
-      uint32_t ph_w1e[2] = {0, 0}, ph_ine[kInStages];
-      for (int s = 0; s < kInStages; ++s) ph_ine[s] = 0;
+      uint32_t ph_w1e = 0, ph_ine = 0;   // phase bits (bit i = parity to wait for on barrier i): registers, not arrays
       for (long t = t_begin; t < t_end; ++t) {
         walker_seek(w, t);
         if (w.g != cur_g) {
           const int b = nchg & 1;
-          if (nchg >= 2) { mbar_wait(&w1_empty[b], ph_w1e[b]); ph_w1e[b] ^= 1; }
-          mbar_arrive_expect_tx(&w1_full[b], w1_buf_bytes);
+          if (nchg >= 2) { mbar_wait(&w1_empty[b], (ph_w1e >> b) & 1u); ph_w1e ^= 1u << b; }
+          mbar_arrive_expect_tx_e(&w1_full[b], w1_buf_bytes);
           for (int m = 0; m < NMLP; ++m)
             for (int at = 0; at < K1g / 64; ++at)
-              tma_load_3d(s_w1 + (size_t)b * w1_buf_bytes + (size_t)m * w1_mlp_bytes + (size_t)at * COUT * 128,
+              tma_load_3d_e(s_w1 + (size_t)b * w1_buf_bytes + (size_t)m * w1_mlp_bytes + (size_t)at * COUT * 128,
                           &map_w1, &w1_full[b], at * 64, 0, w.g * NMLP + m);
           cur_g = w.g;
           ++nchg;
         }
         const long seq = t - t_begin;
         const int st = (int)(seq % kInStages);
-        if (seq >= kInStages) { mbar_wait(&in_empty[st], ph_ine[st]); ph_ine[st] ^= 1; }
+        if (seq >= kInStages) { mbar_wait(&in_empty[st], (ph_ine >> st) & 1u); ph_ine ^= 1u << st; }
         const int p0 = (int)((t - w.base) * kTileM);
         uint8_t* dst = s_in + (size_t)st * stage_bytes;
-        mbar_arrive_expect_tx(&in_full[st], stage_bytes);
+        mbar_arrive_expect_tx_e(&in_full[st], stage_bytes);
         for (int u = 0; u < 2; ++u) {
-          tma_load_3d(dst + (size_t)u * K1 * 128, &map_x0, &in_full[st], p0 + u * 64, 0, w.g);
+          tma_load_3d_e(dst + (size_t)u * K1 * 128, &map_x0, &in_full[st], p0 + u * 64, 0, w.g);
           if (args.nsrc > 1)
-            tma_load_3d(dst + (size_t)u * K1 * 128 + (size_t)args.k_src[0] * 128, &map_x1, &in_full[st], p0 + u * 64,
+            tma_load_3d_e(dst + (size_t)u * K1 * 128 + (size_t)args.k_src[0] * 128, &map_x1, &in_full[st], p0 + u * 64,
                         0, w.g);
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && V > 0) {
-      // ================= MMA issuer =================
+  } else if (warp == 9) {
+    if (V > 0) {
+      // ================= MMA issuer (whole warp, elected lane issues) =================
       const uint32_t idesc1 = make_idesc(Elem<T>::kFmt, /*A MN-major*/ 1, /*B K-major*/ 0, kTileM, COUT);
       const uint32_t idesc2 = make_idesc(Elem<T>::kFmt, 0, 0, kTileM, COUT);
       Walker w;
       walker_init(w);
       int cur_g = -1, nchg = 0, wbuf = 0;
-      uint32_t ph_w1f[2] = {0, 0}, ph_inf[kInStages], ph_h[kSlots];
-      for (int s = 0; s < kInStages; ++s) ph_inf[s] = 0;
-      for (int s = 0; s < kSlots; ++s) ph_h[s] = 0;
+      uint32_t ph_w1f = 0, ph_inf = 0, ph_h = 0;   // phase bits, one per barrier (kept in registers)
+      // descriptor templates: only the 14-bit start-address field (bits 0-13, units of 16 B) varies per MMA
+      const uint64_t a_d0 = smem_desc_sw128(smem_u32(s_in), (uint32_t)K1 * 128u, 1024u);   // MN-major activations
+      const uint64_t b_d0 = smem_desc_sw128(smem_u32(s_w1), 16u, 1024u);                   // K-major weights
+      const uint32_t a_desc_lo0 = (uint32_t)a_d0, a_desc_hi = (uint32_t)(a_d0 >> 32);
+      const uint32_t w1_desc_lo0 = (uint32_t)b_d0, b_desc_hi = (uint32_t)(b_d0 >> 32);
+      const uint32_t wh_desc_lo0 = (uint32_t)smem_desc_sw128(smem_u32(s_wh), 16u, 1024u);
       if (depth > 1) mbar_wait(wh_full, 0);
+      TIMING_DECL;
       for (long v0 = 0; v0 < V; v0 += kSlots) {
+#pragma unroll 1
         for (int l = 0; l < depth; ++l) {
+#pragma unroll 1
           for (int s = 0; s < kSlots; ++s) {
             const long v = v0 + s;
             if (v >= V) break;
             const long seq = v / NMLP;
             const int m = (int)(v % NMLP);
             const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
+            TIMING_MARK(0);
             if (l == 0) {
               const int st = (int)(seq % kInStages);
               if (m == 0) {
                 walker_seek(w, t_begin + seq);
                 if (w.g != cur_g) {
-                  if (cur_g >= 0) mma_commit(&w1_empty[wbuf]);  // all MMAs that read the old buffer retire first
+                  if (cur_g >= 0) mma_commit_e(&w1_empty[wbuf]);  // all MMAs that read the old buffer retire first
                   wbuf = nchg & 1;
-                  mbar_wait(&w1_full[wbuf], ph_w1f[wbuf]);
-                  ph_w1f[wbuf] ^= 1;
+                  mbar_wait(&w1_full[wbuf], (ph_w1f >> wbuf) & 1u);
+                  ph_w1f ^= 1u << wbuf;
                   cur_g = w.g;
                   ++nchg;
                 }
-                mbar_wait(&in_full[st], ph_inf[st]);
-                ph_inf[st] ^= 1;
+                mbar_wait(&in_full[st], (ph_inf >> st) & 1u);
+                ph_inf ^= 1u << st;
               }
+              TIMING_MARK(1);
               if (v >= kSlots) {  // slot reuse: previous occupant's accumulator must be drained
-                mbar_wait(&h_ready[s], ph_h[s]);
-                ph_h[s] ^= 1;
+                mbar_wait(&h_ready[s], (ph_h >> s) & 1u);
+                ph_h ^= 1u << s;
               }
+              TIMING_MARK(2);
               tc_fence_after();
-              const uint32_t a_base = smem_u32(s_in + (size_t)st * stage_bytes);
-              const uint32_t w1_base = smem_u32(s_w1 + (size_t)wbuf * w1_buf_bytes + (size_t)m * w1_mlp_bytes);
-              for (int k = 0; k < K1 / 16; ++k) {
-                const uint64_t ad = smem_desc_sw128(a_base + (uint32_t)k * 2048u, (uint32_t)K1 * 128u, 1024u);
-                const uint64_t bd = smem_desc_sw128(w1_base + (uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u,
-                                                    16u, 1024u);
-                mma_ss(d_tmem, ad, bd, idesc1, k > 0 ? 1u : 0u);
+              {
+                uint32_t a_lo = a_desc_lo0 + (uint32_t)st * (stage_bytes >> 4);
+                uint32_t b_lo = w1_desc_lo0 + ((uint32_t)wbuf * w1_buf_bytes + (uint32_t)m * w1_mlp_bytes >> 4);
+                const int ksteps = K1 / 16;
+#pragma unroll 1
+                for (int k = 0; k < ksteps; ++k) {
+                  mma_ss2_e(d_tmem, a_lo, a_desc_hi, b_lo, b_desc_hi, idesc1, k > 0 ? 1u : 0u);
+                  a_lo += 2048u >> 4;                                       // next 16 K-rows of the MN-major tile
+                  b_lo += ((k & 3) == 3) ? ((COUT * 128u - 96u) >> 4) : (32u >> 4);  // next K atom / next 32 B
+                }
               }
-              if (m == NMLP - 1) mma_commit(&in_empty[st]);
-              mma_commit(&mma_done[s]);
+              if (m == NMLP - 1) mma_commit_e(&in_empty[st]);
+              mma_commit_e(&mma_done[s]);
+              TIMING_MARK(3);
             } else {
-              mbar_wait(&h_ready[s], ph_h[s]);
-              ph_h[s] ^= 1;
+              mbar_wait(&h_ready[s], (ph_h >> s) & 1u);
+              ph_h ^= 1u << s;
+              TIMING_MARK(2);
               tc_fence_after();
-              const uint32_t wl = smem_u32(s_wh + (size_t)(m * (depth - 1) + (l - 1)) * wh_mat_bytes);
-              for (int k = 0; k < COUT / 16; ++k) {
-                const uint64_t bd = smem_desc_sw128(wl + (uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u,
-                                                    16u, 1024u);
-                mma_ts(d_tmem, d_tmem + COUT + (uint32_t)k * 8u, bd, idesc2, k > 0 ? 1u : 0u);
+              TIMING_MARK(3);
+              {
+                const uint32_t wl_lo = wh_desc_lo0 + (uint32_t)(m * (depth - 1) + (l - 1)) * (wh_mat_bytes >> 4);
+#pragma unroll
+                for (int k = 0; k < COUT / 16; ++k)
+                  mma_ts2_e(d_tmem, d_tmem + COUT + (uint32_t)k * 8u,
+                          wl_lo + (((uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u) >> 4), b_desc_hi, idesc2,
+                          k > 0 ? 1u : 0u);
               }
-              mma_commit(&mma_done[s]);
+              TIMING_MARK(4);
+              mma_commit_e(&mma_done[s]);
+              TIMING_MARK(5);
             }
           }
         }
       }
+      TIMING_FLUSH(0, lane == 0);
     }
   } else {
     // ================= epilogue groups =================
-    const int eg = (warp - 2) / 4;           // 0: slots 0,2   1: slots 1,3
+    const int eg = warp / 4;                 // 0: slots 0,2   1: slots 1,3
     const int quad = warp % 4;               // TMEM lane quadrant this warp may access
     const int pix_in_tile = quad * 32 + lane;
-    uint32_t ph_mma[kSlots];
-    for (int s = 0; s < kSlots; ++s) ph_mma[s] = 0;
+    uint32_t ph_mma = 0;                     // phase bits of mma_done[s]
     // per-thread statistics over the pixels this thread has seen: sums in registers, sums of squares in
     // this thread's TMEM lane (keeps the epilogue inside the 168-register budget of a 10-warp CTA)
     float acc_s[COUT];
@@ -480,84 +515,106 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     int acc_g = -1, acc_m = 0;
     Walker w;
     walker_init(w);
-    int slot_g[kSlots / 2] = {0, 0};
-    long slot_base[kSlots / 2] = {0, 0};
+    int slot_g0 = 0, slot_g1 = 0;            // (graph, first tile of graph) of the tile in this group's two slots
+    long slot_base0 = 0, slot_base1 = 0;
 
+    // Column sums over the warp's 32 lanes with a transposing butterfly: every stage halves the number of
+    // live values per lane (62 shuffles for 64 channels instead of 320); afterwards lane L holds the
+    // totals of channels {2*rev-ish(L), +1} -- see the index computation in flush_stats.
+    auto warp_reduce64 = [&](float (&v)[COUT]) {
+#pragma unroll
+      for (int half = COUT / 2, o = 16; o >= 1 && half >= 1; half >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float keep = up ? v[i + half] : v[i];
+          const float send = up ? v[i] : v[i + half];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+    };
     auto flush_stats = [&]() {
-      if (acc_g < 0) return;
       double* dst = args.stat_acc + ((long)acc_g * NMLP + acc_m) * COUT * 2;
+      float qv[COUT];
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 16) {
         uint32_t qq[16];
         tmem_ld16(q_addr + (uint32_t)c0, qq);
         tmem_wait_ld();
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          float a = acc_s[c0 + u], q = __uint_as_float(qq[u]);
-          for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
-          }
-          if (lane == ((c0 + u) & 31)) {
-            atomicAdd(dst + 2 * (c0 + u), (double)a);
-            atomicAdd(dst + 2 * (c0 + u) + 1, (double)q);
-          }
-          acc_s[c0 + u] = 0.f;
-          qq[u] = 0u;
-        }
+        for (int u = 0; u < 16; ++u) { qv[c0 + u] = __uint_as_float(qq[u]); qq[u] = 0u; }
         tmem_st16(q_addr + (uint32_t)c0, qq);
       }
+      warp_reduce64(acc_s);
+      warp_reduce64(qv);
+      // after the 5 stages a lane owns COUT/32 consecutive-stride channels: stage with offset o selected
+      // the upper half (of size COUT/2, COUT/4, ...) when (lane & o) != 0
+      constexpr int kLeft = COUT / 32;
+      int cbase = 0;
+#pragma unroll
+      for (int half = COUT / 2, o = 16; o >= 1; half >>= 1, o >>= 1)
+        if (lane & o) cbase += half;
+#pragma unroll
+      for (int i = 0; i < kLeft; ++i) {
+        atomicAdd(dst + 2 * (cbase + i), (double)acc_s[i]);
+        atomicAdd(dst + 2 * (cbase + i) + 1, (double)qv[i]);
+      }
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc_s[c] = 0.f;
       tmem_wait_st();
     };
 
+    TIMING_DECL;
     for (long v0 = 0; v0 < V; v0 += kSlots) {
+#pragma unroll 1
       for (int l = 0; l < depth; ++l) {
+#pragma unroll 1
         for (int s = eg; s < kSlots; s += 2) {
           const long v = v0 + s;
           if (v >= V) break;
+          TIMING_MARK(0);
           const long seq = v / NMLP;
           const int m = (int)(v % NMLP);
           const bool last = (l == depth - 1);
           const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * kSlotW);
           // the walker only moves forward: resolve (graph, first tile of graph) once per virtual tile, at
           // layer 0, and remember it per slot for the later layers of the same tile
+          const bool second = s >= 2;
           if (l == 0) {
             walker_seek(w, t_begin + seq);
-            slot_g[s >> 1] = w.g;
-            slot_base[s >> 1] = w.base;
+            if (second) { slot_g1 = w.g; slot_base1 = w.base; } else { slot_g0 = w.g; slot_base0 = w.base; }
           }
-          const int g = slot_g[s >> 1];
-          const long gbase = slot_base[s >> 1];
-          mbar_wait(&mma_done[s], ph_mma[s]);
-          ph_mma[s] ^= 1;
+          const int g = second ? slot_g1 : slot_g0;
+          const long gbase = second ? slot_base1 : slot_base0;
+          mbar_wait(&mma_done[s], (ph_mma >> s) & 1u);
+          ph_mma ^= 1u << s;
+          TIMING_MARK(1);
           tc_fence_after();
           if (!last) {
             const float* bias = (l == 0) ? (args.bias1 + ((long)g * NMLP + m) * COUT) : args.bias[m][l];
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 16) {
-              uint32_t r[16];
-              tmem_ld16(lane_addr + (uint32_t)c0, r);
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+              uint32_t r[32];
+              tmem_ld32(lane_addr + (uint32_t)c0, r);
               tmem_wait_ld();
-              uint32_t h[8];
+              uint32_t h[16];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 8; ++u) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * u));
-                const float x0 = fmaxf(__uint_as_float(r[4 * u]) + b4.x, 0.f);
-                const float x1 = fmaxf(__uint_as_float(r[4 * u + 1]) + b4.y, 0.f);
-                const float x2 = fmaxf(__uint_as_float(r[4 * u + 2]) + b4.z, 0.f);
-                const float x3 = fmaxf(__uint_as_float(r[4 * u + 3]) + b4.w, 0.f);
-                h[2 * u] = Elem<T>::pack(x0, x1);
-                h[2 * u + 1] = Elem<T>::pack(x2, x3);
+                float x0 = __uint_as_float(r[4 * u]), x1 = __uint_as_float(r[4 * u + 1]);
+                float x2 = __uint_as_float(r[4 * u + 2]), x3 = __uint_as_float(r[4 * u + 3]);
+                add2(x0, x1, b4.x, b4.y);
+                add2(x2, x3, b4.z, b4.w);
+                h[2 * u] = Elem<T>::pack_relu(x0, x1);
+                h[2 * u + 1] = Elem<T>::pack_relu(x2, x3);
               }
-              tmem_st8(lane_addr + (uint32_t)COUT + (uint32_t)(c0 / 2), h);
+              tmem_st16(lane_addr + (uint32_t)COUT + (uint32_t)(c0 / 2), h);
             }
             tmem_wait_st();
+            TIMING_MARK(2);
           } else {
-            if (g != acc_g || m != acc_m) {
-              flush_stats();
-              acc_g = g;
-              acc_m = m;
-            }
+            acc_g = g;
+            acc_m = m;
             const int n = graph_n(args.n_per_graph, g, geo.N);
             // pixel coordinates with 32-bit arithmetic: one division per tile, then at most two row wraps
             const int p0 = (int)(t_begin + seq - gbase) * kTileM;
@@ -620,19 +677,34 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
               for (int c = 0; c < COUT; ++c) o1[(long)c * plane_stride] = ov;
             }
             tmem_wait_st();
+            // flush the per-thread statistics when the next tile this group finishes belongs to another
+            // (graph, MLP) or does not exist -- the only call site of the (large) reduction code
+            {
+              const long vn = (s + 2 < kSlots && v0 + s + 2 < V) ? (v + 2) : (v0 + kSlots + eg);
+              bool flush = vn >= V;
+              if (!flush) {
+                Walker w2 = w;
+                walker_seek(w2, t_begin + vn / NMLP);
+                flush = (w2.g != g) || ((int)(vn % NMLP) != m);
+              }
+              TIMING_MARK(3);
+              if (flush) flush_stats();
+              TIMING_MARK(4);
+            }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&h_ready[s]);
+          TIMING_MARK(5);
         }
       }
     }
-    flush_stats();
+    TIMING_FLUSH(8, warp == 2 && lane == 0);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0) {
+  if (warp == 8) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -713,7 +785,7 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tmem_full = bars + 2 * kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   const Geo geo = args.geo;
 
   long total = 0;
@@ -734,10 +806,12 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
-      prefetch_tensormap(&map_a);
-      prefetch_tensormap(&map_b);
+    {
+      // ================= TMA producer (whole warp, elected lane issues) =================
+      if (lane == 0) {
+        prefetch_tensormap(&map_a);
+        prefetch_tensormap(&map_b);
+      }
       TileWalker tw;
       tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
       int stage = 0;
@@ -750,18 +824,22 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
           uint8_t* sb = sa + 128 * 128;
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)Cfg::kStageBytes);
-          tma_load_3d(sa, &map_a, &full[stage], kt * 64, m * 128, q);
+          mbar_arrive_expect_tx_e(&full[stage], (uint32_t)Cfg::kStageBytes);
+          tma_load_3d_e(sa, &map_a, &full[stage], kt * 64, m * 128, q);
           for (int u = 0; u < BN / 64; ++u)
-            tma_load_3d(sb + (size_t)u * 8192, &map_b, &full[stage], nn * BN + u * 64, kt * 64, q);
+            tma_load_3d_e(sb + (size_t)u * 8192, &map_b, &full[stage], nn * BN + u * 64, kt * 64, q);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
+    {
+      // ================= MMA issuer (whole warp, elected lane issues) =================
       const uint32_t idesc = make_idesc(Elem<T>::kFmt, /*A K-major*/ 0, /*B MN-major*/ 1, 128, BN);
+      const uint64_t a_d0 = smem_desc_sw128(smem_u32(smem), 16u, 1024u);                 // K-major A tile
+      const uint64_t b_d0 = smem_desc_sw128(smem_u32(smem) + 128 * 128, 8192u, 1024u);   // MN-major B tile
+      const uint32_t a_desc_lo0 = (uint32_t)a_d0, a_desc_hi = (uint32_t)(a_d0 >> 32);
+      const uint32_t b_desc_lo0 = (uint32_t)b_d0, b_desc_hi = (uint32_t)(b_d0 >> 32);
       TileWalker tw;
       tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
       int stage = 0;
@@ -778,18 +856,16 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int kt = 0; kt < kts; ++kt) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + 128 * 128;
+          const uint32_t a_lo = a_desc_lo0 + (uint32_t)stage * (Cfg::kStageBytes >> 4);
+          const uint32_t b_lo = b_desc_lo0 + (uint32_t)stage * (Cfg::kStageBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = smem_desc_sw128(sa + (uint32_t)k * 32u, 16u, 1024u);
-            const uint64_t bd = smem_desc_sw128(sb + (uint32_t)k * 2048u, 8192u, 1024u);
-            mma_ss(d_tmem, ad, bd, idesc, (kt > 0 || k > 0) ? 1u : 0u);
-          }
-          mma_commit(&empty[stage]);
+          for (int k = 0; k < 4; ++k)
+            mma_ss2_e(d_tmem, a_lo + (uint32_t)k * (32u >> 4), a_desc_hi, b_lo + (uint32_t)k * (2048u >> 4), b_desc_hi,
+                      idesc, (kt > 0 || k > 0) ? 1u : 0u);
+          mma_commit_e(&empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        mma_commit(&tmem_full[as]);
+        mma_commit_e(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -1387,6 +1463,26 @@ int debug_mlp(int precision, const fgnn_mlp_params& mp, const float* x, float* y
   if (precision == FGNN_FP16) return debug_mlp_t<__half>(mp, x, y, G, N, n_per_graph, ws, ws_bytes, st);
   return fail(FGNN_ERR_INVALID, "precision must be FGNN_BF16 or FGNN_FP16");
 }
+
+#ifdef FGNN_TC_TIMING
+void dump_timing() {
+  unsigned long long h[16];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
+  const char* mma[6] = {"loop/index", "wait in_full/w1", "wait h_ready", "L1 issue+commit / fence", "hidden: 4 MMA issue", "hidden: commit"};
+  const char* epi[6] = {"loop/index", "wait mma_done", "hidden epilogue", "final epilogue", "stats flush", "fence+arrive"};
+  unsigned long long tm = 0, te = 0;
+  for (int i = 0; i < 6; ++i) { tm += h[i]; te += h[8 + i]; }
+  printf("MMA issuer (sum over CTAs, cycles):\n");
+  for (int i = 0; i < 6; ++i) printf("  %-24s %14llu %5.1f%%\n", mma[i], h[i], 100.0 * h[i] / (tm ? tm : 1));
+  printf("epilogue warp 2 (sum over CTAs, cycles):\n");
+  for (int i = 0; i < 6; ++i) printf("  %-18s %14llu %5.1f%%\n", epi[i], h[8 + i], 100.0 * h[8 + i] / (te ? te : 1));
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_tc_timing, z, sizeof(z));
+}
+#else
+void dump_timing() {}
+#endif
 
 }  // namespace tc
 }  // namespace fgnn

@@ -18,5 +18,7 @@ size_t debug_mlp_workspace_bytes(int G, int c_in, int c_out, int depth, int N);
 int debug_mlp(int precision, const fgnn_mlp_params& mp, const float* x, float* y, int G, int N,
               const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
 
+void dump_timing();
+
 }  // namespace tc
 }  // namespace fgnn

@@ -168,6 +168,10 @@ void fgnn_profile_enable(int on);
 void fgnn_profile_reset(void);
 int fgnn_profile_read(int32_t kind, double* total_ms, int64_t* launches);
 
+/* Bring-up aid: prints the per-role cycle accounting of the conv-chain kernel when the library was
+ * built with -DFGNN_TC_TIMING; a no-op otherwise. */
+void fgnn_debug_dump_timing(void);
+
 /* Diagnostics for the tensor-core building blocks (tests call these to check each kernel in
  * isolation against the fp32 operators): 16-bit planes are (G*C) planes of pitch_rows x pitch_cols. */
 int fgnn_debug_tc_matmul(int32_t precision, const float* a, const float* b, float* out, int32_t G,
