@@ -31,7 +31,16 @@ __global__ void transpose_pad_kernel(const float* __restrict__ w, float* __restr
   wt[idx] = (o < co) ? w[o * ci + i] : 0.f;
 }
 
+// out[i][o] = w[i * co + o] for o < co, 0 for the padding columns (row-padded copy)
+__global__ void pad_rows_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int co, int cop) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cop) return;
+  int i = idx / cop, o = idx % cop;
+  out[idx] = (o < co) ? w[i * co + o] : 0.f;
+}
+
 struct ChainArgs {
+  int relu_last;                    // apply ReLU after the last layer too (used when layers run one at a time)
   int depth;
   int c_in;
   int c_out;
@@ -71,7 +80,7 @@ conv_chain_fwd_kernel(ChainArgs a, const float* __restrict__ x, float* __restric
     for (int co0 = 0; co0 < a.cop; co0 += 8) {
       float acc[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] = (co0 + u < a.c_out) ? __ldg(bk + co0 + u) : 0.f;
+      for (int u = 0; u < 8; ++u) acc[u] = (bk != nullptr && co0 + u < a.c_out) ? __ldg(bk + co0 + u) : 0.f;
       for (int ci = 0; ci < cin; ++ci) {
         float v = (k == 0) ? (valid ? __ldg(xg + (long)ci * P + p) : 0.f) : in[ci * kPixThreads + t];
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (long)ci * a.cop + co0));
@@ -91,7 +100,8 @@ conv_chain_fwd_kernel(ChainArgs a, const float* __restrict__ x, float* __restric
       } else if (inb) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (co0 + u < a.c_out) z[((long)g * a.c_out + co0 + u) * P + p] = valid ? acc[u] : 0.f;
+          if (co0 + u < a.c_out)
+            z[((long)g * a.c_out + co0 + u) * P + p] = valid ? (a.relu_last ? fmaxf(acc[u], 0.f) : acc[u]) : 0.f;
       }
     }
     in = out;
@@ -400,6 +410,43 @@ int check_dims(int G, int C, int N) {
 
 }  // namespace
 
+// ---- pieces shared with fgnn_f32_bwd.cu ---------------------------------------------------------
+int run_conv1x1(const float* w, const float* b, int c_in, int c_out, bool transpose_w, bool relu, const float* x,
+                float* y, float* wt_scratch, int G, int N, const int32_t* n_per_graph, cudaStream_t st) {
+  // y[g,co,p] = sum_ci W'[co,ci] x[g,ci,p] (+ b[co]) (optionally ReLU) on valid pixels, 0 elsewhere.
+  // transpose_w: W' = w^T where w is stored (c_in, c_out) row-major, i.e. the backward-data conv.
+  ChainArgs a;
+  a.relu_last = relu ? 1 : 0;
+  a.depth = 1;
+  a.c_in = c_in;
+  a.c_out = c_out;
+  a.cop = (c_out + 7) / 8 * 8;
+  const int total = c_in * a.cop;
+  if (!transpose_w) {
+    transpose_pad_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, wt_scratch, c_out, c_in, a.cop);
+  } else {
+    // w is (c_in rows, c_out cols): already "wt" up to row padding -> transpose_pad of its transpose == pad rows
+    // implemented as transpose_pad with swapped roles: out[i][o] = w[i*c_out + o]
+    pad_rows_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, wt_scratch, c_in, c_out, a.cop);
+  }
+  FGNN_LAUNCHED();
+  a.wt[0] = wt_scratch;
+  a.b[0] = b;
+  const size_t smem = (size_t)2 * a.cop * kPixThreads * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FGNN_CUDA(cudaFuncSetAttribute(conv_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   2 * kMaxC * kPixThreads * (int)sizeof(float)));
+    attr_set = true;
+  }
+  FGNN_CHECK_ARG(c_out <= kMaxC, "conv1x1: c_out %d unsupported (max %d)", c_out, kMaxC);
+  long P = (long)N * N;
+  dim3 grid((unsigned)((P + kPixThreads - 1) / kPixThreads), G);
+  conv_chain_fwd_kernel<<<grid, kPixThreads, smem, st>>>(a, x, y, N, n_per_graph);
+  FGNN_LAUNCHED();
+  return FGNN_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
@@ -407,8 +454,15 @@ size_t mlp_workspace_bytes(int G, int c_in, int c_out, int depth, int N) {
   Arena ar(nullptr, 0);
   const int cop = (c_out + 7) / 8 * 8;
   for (int k = 0; k < depth; ++k) ar.take<float>((size_t)(k == 0 ? c_in : c_out) * cop);
-  // backward scratch: per-(g,c) reductions
+  // backward scratch: per-(g,c) reductions + (depth + 2) activation tensors for a chunk of graphs
   ar.take<float>((size_t)G * c_out * 2);
+  const int cmax = c_out > c_in ? c_out : c_in;
+  ar.take<float>((size_t)cmax * ((cmax + 7) / 8 * 8));
+  const size_t per_graph = (size_t)(depth + 2) * cmax * N * N * sizeof(float) + 256 * (depth + 2);
+  size_t graphs = ((size_t)1 << 30) / per_graph;
+  if (graphs < 1) graphs = 1;
+  if (graphs > (size_t)G) graphs = G;
+  ar.take<char>(graphs * per_graph + 4096);
   return align_up(ar.off, 256);
 }
 
@@ -416,6 +470,7 @@ static int prepare_chain(const fgnn_mlp_params& p, ChainArgs& a, Arena& ar, cuda
   FGNN_CHECK_ARG(p.depth >= 1 && p.depth <= FGNN_MAX_DEPTH, "depth %d out of range", p.depth);
   FGNN_CHECK_ARG(p.c_out >= 1 && p.c_out <= kMaxC, "c_out %d unsupported (max %d)", p.c_out, kMaxC);
   FGNN_CHECK_ARG(p.c_in >= 1 && p.c_in <= kMaxCin, "c_in %d unsupported (max %d)", p.c_in, kMaxCin);
+  a.relu_last = 0;
   a.depth = p.depth;
   a.c_in = p.c_in;
   a.c_out = p.c_out;

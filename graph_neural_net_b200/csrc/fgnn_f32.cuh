@@ -6,6 +6,10 @@
 namespace fgnn {
 namespace f32 {
 
+// single 1x1 conv layer (shared by forward recomputation and backward-data in fgnn_f32_bwd.cu)
+int run_conv1x1(const float* w, const float* b, int c_in, int c_out, bool transpose_w, bool relu, const float* x,
+                float* y, float* wt_scratch, int G, int N, const int32_t* n_per_graph, cudaStream_t st);
+
 // workspace layout helper for one MLP call
 size_t mlp_workspace_bytes(int G, int c_in, int c_out, int depth, int N);
 

@@ -1,0 +1,79 @@
+"""Data-parallel training step for the siamese 2-FGNN (BASELINE.json configs[4]).
+
+The reference trains through pytorch_lightning.Trainer (commander_explore.py:120-123), whose only
+multi-GPU mechanism is Lightning's default DDP.  Here one process drives one GPU, the batch of graph
+pairs is sharded across ranks, and a training step issues exactly ONE collective: an all-reduce (sum)
+of a flat fp32 buffer holding every parameter gradient plus the two scalars of the loss
+(sum of row cross-entropies, number of rows).  The loss of toolbox/losses.py:20-34 divides by the
+GLOBAL number of rows, so each rank back-propagates its un-normalised local sum and the division
+happens once, after the reduction -- exact for ragged shards too.  Forward needs no collective:
+GraphNorm statistics are per (graph, channel) (models/layers.py:72-73).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def flat_gradient_allreduce(params: Iterable[torch.nn.Parameter], extras: torch.Tensor,
+                            group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-reduce (sum) every `p.grad` and the 1-D tensor `extras` in ONE flat buffer.
+
+    Gradients are written back in place; the reduced extras are returned.  Works on any backend
+    (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    plist: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+    if not plist:
+        raise ValueError("no trainable parameters")
+    dev = plist[0].device
+    sizes = [p.numel() for p in plist]
+    flat = torch.empty(sum(sizes) + extras.numel(), dtype=torch.float32, device=dev)
+    off = 0
+    for p, n in zip(plist, sizes):
+        if p.grad is None:
+            flat[off:off + n].zero_()
+        else:
+            flat[off:off + n].copy_(p.grad.reshape(-1))
+        off += n
+    flat[off:].copy_(extras.to(device=dev, dtype=torch.float32))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p, n in zip(plist, sizes):
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return flat[off:].clone()
+
+
+def shard_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of `total` pairs for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def train_step(model, optimizer, x1, x2, group: Optional[dist.ProcessGroup] = None):
+    """One data-parallel step on this rank's shard (x1, x2: {'input': (b,2,N,N)} dicts or MaskedTensor
+    dicts).  Returns (global loss, global #correct, global #rows) as Python numbers."""
+    from . import _ops
+    from .toolbox.losses import _as_batch
+
+    optimizer.zero_grad(set_to_none=True)
+    scores = model(x1, x2)
+    plain, n_dev, sizes = _as_batch(scores)
+    ce, correct = _ops.CrossEntropyIdentityFunction.apply(plain, n_dev)
+    local_sum = ce.sum()
+    local_sum.backward()                                   # un-normalised: d(sum CE_local)/d theta
+    extras = torch.stack((local_sum.detach(), sizes.sum(), correct.sum().to(torch.float32)))
+    ce_all, n_all, ok_all = flat_gradient_allreduce(model.parameters(), extras, group).tolist()
+    inv = 1.0 / max(n_all, 1.0)
+    for p in model.parameters():
+        if p.grad is not None:
+            p.grad.mul_(inv)                               # loss = sum CE / sum n  (losses.py:12-13, 34)
+    optimizer.step()
+    return ce_all * inv, int(round(ok_all)), int(round(n_all))

@@ -152,3 +152,39 @@ def test_head_backward_matches_autograd():
 def test_cpu_tensors_are_rejected():
     with pytest.raises(pkg.FgnnError):
         Matmul()(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
+
+
+@pytest.mark.parametrize("name", ["tiny_er12_c8", "cfg1_er50_c32"])
+def test_fp32_training_gradients_match_reference_autograd(name):
+    """loss.backward() through every fp32 CUDA operator vs the gradients the reference's autograd
+    produced for the same weights and inputs (tests/golden, written by oracle/make_golden.py)."""
+    z = load_golden(name)
+    model = build_model(z)
+    x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    scores = model({"input": x1}, {"input": x2})
+    loss = triplet_loss("mean")(scores)
+    assert abs(float(loss) - float(z["loss_mean"])) < 1e-4
+    loss.backward()
+    worst = 0.0
+    for k, p in model.named_parameters():
+        g = z["grad/" + k]
+        assert p.grad is not None, k
+        if np.abs(g).max() < 1e-6:                       # last-conv biases: mathematically zero
+            assert float(p.grad.abs().max()) < 1e-5, k
+        else:
+            e = rel_fro(p.grad.cpu(), g)
+            worst = max(worst, e)
+            assert e < 5e-3, (k, e)
+    print(f"{name}: worst parameter-gradient rel err {worst:.2e}")
+
+
+def test_fp32_train_step_reduces_loss():
+    """A few Adam steps of graph_neural_net_b200.training.train_step (world size 1) on one batch."""
+    from graph_neural_net_b200.training import train_step
+    z = load_golden("tiny_er12_c8")
+    model = build_model(z)
+    opt = model.configure_optimizers()["optimizer"]
+    x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    losses = [train_step(model, opt, {"input": x1}, {"input": x2})[0] for _ in range(8)]
+    assert abs(losses[0] - float(z["loss_mean"])) < 1e-4
+    assert losses[-1] < losses[0]
