@@ -218,8 +218,10 @@ class CrossEntropyIdentityFunction(torch.autograd.Function):
         ce = torch.empty(G, device=scores.device, dtype=torch.float32)
         correct = torch.empty(G, device=scores.device, dtype=torch.int32)
         lse = torch.empty((G, N), device=scores.device, dtype=torch.float32)
+        ws = L.workspace(scores.device, lib.fgnn_ce_workspace_bytes(G, N))
         L.check(lib.fgnn_ce_argmax_fwd_f32(L.ptr(scores), L.ptr(ce), L.ptr(correct), L.ptr(lse), G, N,
-                                           _npg(n_dev), L.stream_ptr(scores.device)), "fgnn_ce_argmax_fwd_f32")
+                                           _npg(n_dev), L.ptr(ws), ws.numel(), L.stream_ptr(scores.device)),
+                "fgnn_ce_argmax_fwd_f32")
         ctx.save_for_backward(scores, lse, n_dev if n_dev is not None else torch.empty(0))
         ctx.has_n = n_dev is not None
         ctx.mark_non_differentiable(correct)

@@ -218,9 +218,13 @@ int fgnn_scores_bwd_f32(const float* e1, const float* e2, const float* dscores, 
   return f32::scores_bwd(e1, e2, dscores, de1, de2, G, C, N, n_per_graph, (cudaStream_t)stream);
 }
 
+size_t fgnn_ce_workspace_bytes(int32_t G, int32_t N) { return (size_t)G * N * 8 + 1024; }
+
 int fgnn_ce_argmax_fwd_f32(const float* scores, float* ce_sum, int32_t* correct, float* row_lse,
-                           int32_t G, int32_t N, const int32_t* n_per_graph, void* stream) {
-  return f32::ce_argmax_fwd(scores, ce_sum, correct, row_lse, G, N, n_per_graph, (cudaStream_t)stream);
+                           int32_t G, int32_t N, const int32_t* n_per_graph, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return f32::ce_argmax_fwd(scores, ce_sum, correct, row_lse, G, N, n_per_graph, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
 }
 
 int fgnn_ce_bwd_f32(const float* scores, const float* row_lse, const float* coef, float* dscores,

@@ -328,16 +328,18 @@ scores_bwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2, co
 // losses.py:27-34 / metrics.py:125-134 without the host loop.  Deterministic reduction.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ce_argmax_fwd_kernel(const float* __restrict__ s, float* __restrict__ ce_sum, int32_t* __restrict__ correct,
-                     float* __restrict__ row_lse, int N, const int32_t* __restrict__ n_per_graph) {
-  const int g = blockIdx.x;
+ce_argmax_rows_kernel(const float* __restrict__ s, float* __restrict__ row_ce, int32_t* __restrict__ row_ok,
+                      float* __restrict__ row_lse, int N, const int32_t* __restrict__ n_per_graph) {
+  // one warp per row: row_ce[g,i] = lse_i - s_ii, row_ok[g,i] = (argmax_j s_ij == i); padded rows -> 0
+  const int g = blockIdx.y;
   const int n = graph_n(n_per_graph, g, N);
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
-  const float* sg = s + (long)g * N * N;
-  float ce = 0.f;
+  const int lane = threadIdx.x % 32;
+  const int i = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (i >= N) return;
+  float ce = 0.f, lse = 0.f;
   int ok = 0;
-  for (int i = warp; i < n; i += nw) {
-    const float* r = sg + (long)i * N;
+  if (i < n) {
+    const float* r = s + ((long)g * N + i) * N;
     float m = -INFINITY;
     int am = 0;
     for (int j = lane; j < n; j += 32) {
@@ -352,25 +354,43 @@ ce_argmax_fwd_kernel(const float* __restrict__ s, float* __restrict__ ce_sum, in
     float se = 0.f;
     for (int j = lane; j < n; j += 32) se += expf(r[j] - m);
     for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-    float lse = m + logf(se);
-    if (lane == 0) {
-      ce += lse - r[i];
-      ok += (am == i);
-      if (row_lse) row_lse[(long)g * N + i] = lse;
-    }
+    lse = m + logf(se);
+    ce = lse - r[i];
+    ok = (am == i);
   }
-  if (row_lse)
-    for (int i = n + threadIdx.x; i < N; i += blockDim.x) row_lse[(long)g * N + i] = 0.f;
-  __shared__ float sce[32];
-  __shared__ int sok[32];
-  if (lane == 0) { sce[warp] = ce; sok[warp] = ok; }
+  if (lane == 0) {
+    row_ce[(long)g * N + i] = ce;
+    row_ok[(long)g * N + i] = ok;
+    if (row_lse) row_lse[(long)g * N + i] = lse;
+  }
+}
+
+// deterministic per-graph reduction of the per-row results (fixed order, one CTA per graph)
+__global__ void __launch_bounds__(256)
+ce_argmax_reduce_kernel(const float* __restrict__ row_ce, const int32_t* __restrict__ row_ok,
+                        float* __restrict__ ce_sum, int32_t* __restrict__ correct, int N) {
+  const int g = blockIdx.x;
+  float t = 0.f;
+  int k = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    t += row_ce[(long)g * N + i];
+    k += row_ok[(long)g * N + i];
+  }
+  __shared__ float st[256];
+  __shared__ int sk[256];
+  st[threadIdx.x] = t;
+  sk[threadIdx.x] = k;
   __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      st[threadIdx.x] += st[threadIdx.x + o];
+      sk[threadIdx.x] += sk[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    int k = 0;
-    for (int w = 0; w < nw; ++w) { t += sce[w]; k += sok[w]; }
-    ce_sum[g] = t;
-    if (correct) correct[g] = k;
+    ce_sum[g] = st[0];
+    if (correct) correct[g] = sk[0];
   }
 }
 
@@ -580,10 +600,17 @@ int scores_bwd(const float* e1, const float* e2, const float* ds, float* de1, fl
 }
 
 int ce_argmax_fwd(const float* scores, float* ce_sum, int32_t* correct, float* row_lse, int G, int N,
-                  const int32_t* n_per_graph, cudaStream_t st) {
+                  const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (int e = check_dims(G, 1, N)) return e;
-  FGNN_CHECK_ARG(scores && ce_sum, "null pointer");
-  ce_argmax_fwd_kernel<<<G, 256, 0, st>>>(scores, ce_sum, correct, row_lse, N, n_per_graph);
+  FGNN_CHECK_ARG(scores && ce_sum && ws, "null pointer");
+  FGNN_CHECK_ARG(G <= 65535, "G=%d exceeds grid.y limit", G);
+  Arena ar(ws, ws_bytes);
+  float* row_ce = ar.take<float>((size_t)G * N);
+  int32_t* row_ok = ar.take<int32_t>((size_t)G * N);
+  if (!ar.ok()) return fail(FGNN_ERR_WORKSPACE, "ce workspace too small");
+  ce_argmax_rows_kernel<<<dim3(ceil_div(N, 8), G), 256, 0, st>>>(scores, row_ce, row_ok, row_lse, N, n_per_graph);
+  FGNN_LAUNCHED();
+  ce_argmax_reduce_kernel<<<G, 256, 0, st>>>(row_ce, row_ok, ce_sum, correct, N);
   FGNN_LAUNCHED();
   return FGNN_OK;
 }

@@ -31,7 +31,7 @@ int scores_fwd(const float* e1, const float* e2, float* scores, int G, int C, in
 int scores_bwd(const float* e1, const float* e2, const float* ds, float* de1, float* de2, int G, int C,
                int N, const int32_t* n_per_graph, cudaStream_t st);
 int ce_argmax_fwd(const float* scores, float* ce_sum, int32_t* correct, float* row_lse, int G, int N,
-                  const int32_t* n_per_graph, cudaStream_t st);
+                  const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
 int ce_bwd(const float* scores, const float* row_lse, const float* coef, float* ds, int G, int N,
            const int32_t* n_per_graph, cudaStream_t st);
 // out (G,Ca+Cb,N,N) = cat(a (G,Ca,N,N), b (G,Cb,N,N)) along channels  (models/layers.py:145-146)

@@ -141,37 +141,36 @@ struct FoldArgs {
   int c_out, K1g;
 };
 template <typename T>
-__global__ void fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf) {
-  const int g = blockIdx.x;
+__global__ void __launch_bounds__(256)
+fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf) {
+  const int g = blockIdx.x, m = blockIdx.y;
   const int cin = a.c[0] + (a.nsrc > 1 ? a.c[1] : 0);
-  for (int m = 0; m < a.nmlp; ++m) {
-    T* wg = wf + ((long)g * a.nmlp + m) * a.c_out * a.K1g;
-    const float* w = a.w[m];
-    for (int idx = threadIdx.x; idx < a.c_out * a.K1g; idx += blockDim.x) {
-      int co = idx / a.K1g, k = idx % a.K1g;
-      float v = 0.f;
-      int col = 0;
-      for (int s = 0; s < a.nsrc; ++s) {
-        int ch = k - a.koff[s];
-        if (ch >= 0 && ch < a.c[s]) {
-          float sc = a.coef[s] ? a.coef[s][((long)g * a.c[s] + ch) * 2] : 1.f;
-          v = w[co * cin + col + ch] * sc;
-        }
-        col += a.c[s];
-      }
-      wg[idx] = Elem<T>::from_float(v);
-    }
-    for (int co = threadIdx.x; co < a.c_out; co += blockDim.x) {
-      float acc = a.b[m][co];
-      int col = 0;
-      for (int s = 0; s < a.nsrc; ++s) {
-        if (a.coef[s])
-          for (int ch = 0; ch < a.c[s]; ++ch)
-            acc = fmaf(w[co * cin + col + ch], a.coef[s][((long)g * a.c[s] + ch) * 2 + 1], acc);
-        col += a.c[s];
-      }
-      bf[((long)g * a.nmlp + m) * a.c_out + co] = acc;
-    }
+  __shared__ float s_a[512], s_s[512];          // per input column: scale and shift of its source channel
+  for (int col = threadIdx.x; col < cin; col += blockDim.x) {
+    const int s = (col < a.c[0]) ? 0 : 1;
+    const int ch = col - (s ? a.c[0] : 0);
+    s_a[col] = a.coef[s] ? a.coef[s][((long)g * a.c[s] + ch) * 2] : 1.f;
+    s_s[col] = a.coef[s] ? a.coef[s][((long)g * a.c[s] + ch) * 2 + 1] : 0.f;
+  }
+  __syncthreads();
+  T* wg = wf + ((long)g * a.nmlp + m) * a.c_out * a.K1g;
+  const float* w = a.w[m];
+  for (int idx = threadIdx.x; idx < a.c_out * a.K1g; idx += blockDim.x) {
+    const int co = idx / a.K1g, k = idx % a.K1g;
+    float v = 0.f;
+    int col = -1;
+    if (k < a.koff[1] || a.nsrc == 1) { if (k < a.c[0]) col = k; }
+    else if (k - a.koff[1] < a.c[1]) col = a.c[0] + (k - a.koff[1]);
+    if (col >= 0) v = w[co * cin + col] * s_a[col];
+    wg[idx] = Elem<T>::from_float(v);
+  }
+  // folded bias: one warp per output channel
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int co = warp; co < a.c_out; co += blockDim.x / 32) {
+    float acc = 0.f;
+    for (int col = lane; col < cin; col += 32) acc = fmaf(w[co * cin + col], s_s[col], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) bf[((long)g * a.nmlp + m) * a.c_out + co] = a.b[m][co] + acc;
   }
 }
 
@@ -204,9 +203,11 @@ __global__ void finalize_coef_kernel(CoefArgs a, int total) {
 }
 
 // emb[g][c][i] = max_{j<n} (a*y[i][j] + s); rows >= n -> 0   (layers.py:194-203 on folded data, layout C)
+// One warp per row, 16-byte loads (8 elements); hole columns and columns beyond n are masked by index.
 template <typename T>
-__global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ coef, float* __restrict__ emb, int C,
-                            Geo geo, long rows, const int32_t* __restrict__ n_per_graph) {
+__global__ void __launch_bounds__(256)
+pool_kernel(const T* __restrict__ y, const float* __restrict__ coef, float* __restrict__ emb, int C, Geo geo,
+            long rows, const int32_t* __restrict__ n_per_graph) {
   const long row = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   if (row >= rows) return;
   const int lane = threadIdx.x % 32;
@@ -216,12 +217,21 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ c
   const int n = graph_n(n_per_graph, g, geo.N);
   float out = 0.f;
   if (i < n) {
-    const T* r = y + q * geo.PSC + (long)i * geo.NPC;
+    const uint4* r = reinterpret_cast<const uint4*>(y + q * geo.PSC + (long)i * geo.NPC);
+    const int pj_end = (n - 1) + (n - 1) / geo.TN1 + 1;     // one past the last valid physical column
     float mx = -INFINITY, mn = INFINITY;
-    for (int j = lane; j < n; j += 32) {
-      float v = Elem<T>::to_float(r[j + j / geo.TN1]);
-      mx = fmaxf(mx, v);
-      mn = fminf(mn, v);
+    for (int v = lane; v * 8 < pj_end; v += 32) {
+      const uint4 w = __ldg(r + v);
+      const T* e = reinterpret_cast<const T*>(&w);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int pj = v * 8 + u;
+        if (pj < pj_end && (pj & (geo.BN - 1)) != geo.BN - 1) {
+          const float x = Elem<T>::to_float(e[u]);
+          mx = fmaxf(mx, x);
+          mn = fminf(mn, x);
+        }
+      }
     }
     for (int o = 16; o > 0; o >>= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -1149,7 +1159,8 @@ int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int3
   fa.koff[1] = round_up(M.c_src[0], 16);
   fa.c_out = C;
   fa.K1g = round_up(round_up(M.c_src[0], 16) + (M.nsrc > 1 ? round_up(M.c_src[1], 16) : 0), 64);
-  fold_weights_kernel<T><<<G, 256, 0, st>>>(fa, M.wf, M.bf);
+  FGNN_CHECK_ARG(fa.c[0] + fa.c[1] <= 512, "too many input channels for the fold kernel");
+  fold_weights_kernel<T><<<dim3(G, M.nmlp), 256, 0, st>>>(fa, M.wf, M.bf);
   FGNN_LAUNCHED();
   MlpLaunch<T> L{};
   L.nmlp = M.nmlp;

@@ -133,9 +133,12 @@ int fgnn_scores_bwd_f32(const float* e1, const float* e2, const float* dscores, 
 /* Row-softmax cross-entropy against the identity matching + row argmax, one pass
  * (toolbox/losses.py:20-34 and toolbox/metrics.py:118-141 without the per-graph host loop).
  * scores (G,N,N) -> ce_sum[G] (sum_i lse_i - s_ii), correct[G] (#rows with argmax == i),
- * row_lse (G,N) may be NULL (kept for backward). */
+ * row_lse (G,N) may be NULL (kept for backward).  One warp per row + a fixed-order per-graph reduction
+ * (deterministic); workspace: fgnn_ce_workspace_bytes. */
+size_t fgnn_ce_workspace_bytes(int32_t G, int32_t N);
 int fgnn_ce_argmax_fwd_f32(const float* scores, float* ce_sum, int32_t* correct, float* row_lse,
-                           int32_t G, int32_t N, const int32_t* n_per_graph, void* stream);
+                           int32_t G, int32_t N, const int32_t* n_per_graph, void* workspace,
+                           size_t workspace_bytes, void* stream);
 /* dscores[g,i,j] = coef[g] * (softmax(scores[g,i,:])[j] - [i==j]); coef folds the loss
  * reduction and the upstream gradient. */
 int fgnn_ce_bwd_f32(const float* scores, const float* row_lse, const float* coef, float* dscores,
