@@ -80,6 +80,18 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- tcgen05: TMEM management -----------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
@@ -288,6 +300,10 @@ template <> struct Elem<__nv_bfloat16> {
     return *reinterpret_cast<uint32_t*>(&v);
   }
   __device__ static __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __forceinline__ float2 unpack2(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+  }
+  __device__ static __forceinline__ uint16_t bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
   __device__ static __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
 };
 template <> struct Elem<__half> {
@@ -302,6 +318,10 @@ template <> struct Elem<__half> {
     return *reinterpret_cast<uint32_t*>(&v);
   }
   __device__ static __forceinline__ float to_float(__half v) { return __half2float(v); }
+  __device__ static __forceinline__ float2 unpack2(uint32_t w) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  }
+  __device__ static __forceinline__ uint16_t bits(float v) { return __half_as_ushort(__float2half_rn(v)); }
   __device__ static __forceinline__ __half from_float(float v) { return __float2half_rn(v); }
 };
 

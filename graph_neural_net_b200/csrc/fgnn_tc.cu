@@ -12,10 +12,14 @@
 // and into the final max-pool (max(a y + s) = a max(y) + s or a min(y) + s by the sign of a).
 // The row sums r1 = Y1 1 and column sums c2 = 1^T Y2 come out of the matmul itself: the operand
 // layouts carry a row / column of ones per MMA tile,
-//   layout C (block inputs/outputs, Y2, mult): rows i < N, physical column pj = j + j / (BN-1), pitch
-//            NPC = BN * NT; physical columns pj % BN == BN-1 are "holes" (ones in Y2, zero elsewhere);
-//   layout A (Y1): physical row pi = i + i / 127, PRA = 128 * MT rows, pitch NPA = round_up(N, 8);
-//            physical rows pi % 128 == 127 hold ones,
+//   every plane has physical columns pj = j + j / (BN-1) with pitch NPC = BN * NT; physical columns
+//   pj % BN == BN-1 are "holes" (ones in Y2, zero elsewhere), so a 128-pixel tile of the conv kernel is 128
+//   consecutive physical columns in every layout and is written with one TMA store per 64-pixel half;
+//   layout C (block inputs/outputs, mult): rows i < N;
+//   layout A (Y1, the matmul's A operand): physical row i + i / 127, PRA = 128 * MT rows, rows == 127 mod 128
+//            hold ones (zero at hole columns);
+//   layout B (Y2, the matmul's B operand): physical row k + k / (BN-1) -- the matmul's K index is the PHYSICAL
+//            column of Y1 / row of Y2; hole rows are zero, hole columns hold ones,
 // so D[127, :] of every 128 x BN accumulator tile is c2 and D[:, BN-1] is r1, at no extra MMA cost.
 #include "fgnn_tc.cuh"
 #include "fgnn_ptx.cuh"
@@ -36,8 +40,8 @@ constexpr int kTileM = 128;  // pixels per MLP tile / physical rows per matmul t
 constexpr int kTM1 = 127;    // logical rows per matmul tile
 
 struct Geo {
-  int N, BN, TN1, NT, NPC, NPA, MT, PRA, BNLOG;
-  long PSC, PSA;
+  int N, BN, TN1, NT, NPC, MT, PRA, PRB, BNLOG;
+  long PSC, PSA, PSB;
 };
 
 inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -50,57 +54,63 @@ Geo make_geo(int N) {
   g.BNLOG = (g.BN == 64) ? 6 : (g.BN == 128 ? 7 : 8);
   g.NT = (N + g.TN1 - 1) / g.TN1;
   g.NPC = g.BN * g.NT;
-  g.NPA = round_up(N, 8);
   g.MT = (N + kTM1 - 1) / kTM1;
   g.PRA = 128 * g.MT;
   g.PSC = (long)N * g.NPC;
-  g.PSA = (long)g.PRA * g.NPA;
+  g.PRB = (N - 1) + (N - 1) / g.TN1 + 1;   // exactly the physical rows that are written (or zeroed holes): reads beyond are OOB = 0
+  g.PSA = (long)g.PRA * g.NPC;
+  g.PSB = (long)g.PRB * g.NPC;
   return g;
 }
 
 __device__ __forceinline__ int graph_n(const int32_t* n_per_graph, int g, int N) {
   return n_per_graph ? n_per_graph[g] : N;
 }
-// rows of a plane that the conv kernels must cover so that K-loops of the matmul may over-read zeros
-__device__ __forceinline__ int rows_cover(const int32_t* n_per_graph, int g, int N) {
-  if (!n_per_graph) return N;
-  int n = n_per_graph[g];
-  int r = (n + 63) / 64 * 64;
-  return r < N ? r : N;
+// one past the last physical K index (column of Y1 / row of Y2) a graph with n vertices uses
+__device__ __forceinline__ int phys_k_end(int n, int TN1) { return (n - 1) + (n - 1) / TN1 + 1; }
+// logical rows of a plane that the conv kernels must cover so that K-loops of the matmul may over-read zeros
+__device__ __forceinline__ int rows_cover(const int32_t* n_per_graph, int g, const Geo& geo) {
+  if (!n_per_graph) return geo.N;
+  int r = (phys_k_end(n_per_graph[g], geo.TN1) + 63) / 64 * 64;
+  return r < geo.N ? r : geo.N;
 }
 __device__ __forceinline__ long mlp_tiles(const int32_t* n_per_graph, int g, const Geo& geo) {
-  return ((long)rows_cover(n_per_graph, g, geo.N) * geo.NPC + kTileM - 1) / kTileM;
+  return ((long)rows_cover(n_per_graph, g, geo) * geo.NPC + kTileM - 1) / kTileM;
 }
 
 // =============================================================================================
 // small CUDA-core kernels
 // =============================================================================================
 
-// fp32 (G,C,N,N) -> 16-bit planes in layout C (mode 0) or layout A (mode 1).  Padding, holes and
-// the ones row/column are written as zero (only the debug entry points use layout A / ones-free C).
+// fp32 (G,C,N,N) -> 16-bit planes in layout C (mode 0), A (mode 1) or B (mode 2).  Padding, holes and the
+// ones row/column are written as zero (only the debug entry points use layouts A / B).
 template <typename T>
 __global__ void to_planes_kernel(const float* __restrict__ x, T* __restrict__ out, int C, Geo geo, int mode,
                                  const int32_t* __restrict__ n_per_graph) {
   const int gc = blockIdx.y;
   const int g = gc / C;
   const int n = graph_n(n_per_graph, g, geo.N);
-  const long PS = mode == 0 ? geo.PSC : geo.PSA;
-  const int pitch = mode == 0 ? geo.NPC : geo.NPA;
+  const long PS = mode == 0 ? geo.PSC : (mode == 1 ? geo.PSA : geo.PSB);
   for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < PS; p += (long)gridDim.x * blockDim.x) {
-    int pi = (int)(p / pitch), pj = (int)(p % pitch);
-    int i, j;
-    bool hole;
-    if (mode == 0) {
-      hole = (pj % geo.BN) == geo.BN - 1;
-      i = pi;
-      j = pj - pj / geo.BN;
-    } else {
-      hole = (pi % 128) == 127;
-      i = pi - pi / 128;
-      j = pj;
-    }
+    const int pi = (int)(p / geo.NPC), pj = (int)(p % geo.NPC);
+    bool hole = (pj % geo.BN) == geo.BN - 1;
+    const int j = pj - pj / geo.BN;
+    int i = pi;
+    if (mode == 1) { hole = hole || (pi % 128) == 127; i = pi - pi / 128; }
+    if (mode == 2) { hole = hole || (pi % geo.BN) == geo.BN - 1; i = pi - pi / geo.BN; }
     float v = (!hole && i < n && j < n) ? x[((long)gc * geo.N + i) * geo.N + j] : 0.f;
     out[(long)gc * PS + p] = Elem<T>::from_float(v);
+  }
+}
+
+// zero the hole rows of layout-B planes (the conv kernel never writes them; they must contribute 0 to K sums)
+template <typename T>
+__global__ void zero_hole_rows_kernel(T* __restrict__ y, Geo geo) {
+  T* plane = y + (long)blockIdx.y * geo.PSB;
+  const int nholes = geo.PRB / geo.BN;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nholes * geo.NPC; idx += gridDim.x * blockDim.x) {
+    const int h = idx / geo.NPC, col = idx % geo.NPC;
+    plane[(long)(h * geo.BN + geo.BN - 1) * geo.NPC + col] = Elem<T>::from_float(0.f);
   }
 }
 
@@ -255,7 +265,7 @@ pool_kernel(const T* __restrict__ y, const float* __restrict__ coef, float* __re
 // alternate virtual tiles (slot parity).  TMEM slot s: accumulator columns [s*1.5*COUT, +COUT),
 // packed hidden activations in the next COUT/2 columns.
 // =============================================================================================
-enum OutMode { kOutC = 0, kOutA = 1 };
+enum OutMode { kOutC = 0, kOutA = 1, kOutB = 2 };   // output plane layout: rows i / i + i/127 / i + i/(BN-1)
 
 template <typename T>
 struct MlpArgs {
@@ -265,9 +275,9 @@ struct MlpArgs {
   int depth, Kh;
   const float* bias1;                        // [G][NMLP][COUT] folded layer-1 bias
   const float* bias[2][FGNN_MAX_DEPTH];      // per MLP, layer l >= 1 biases
-  T* out[2];                                 // per MLP output planes
-  int out_mode[2];                           // kOutC / kOutA
-  int ones[2];                               // write the ones row/column (Y1 / Y2) instead of zeros
+  T* out[2];                                 // per MLP output planes (direct stores of the ones row only)
+  int out_mode[2];                           // kOutC / kOutA / kOutB
+  int ones[2];                               // kOutA: write the ones rows; kOutB: holes hold ones
   double* stat_acc;                          // [G][NMLP][COUT][2]
   const int32_t* n_per_graph;
 };
@@ -291,19 +301,18 @@ template <int COUT, int NMLP>
 struct MlpSmem {
   static size_t bytes(int K1, int K1g, int depth, int Kh) {
     return 1024 + (size_t)kInStages * K1 * 256 + (size_t)2 * NMLP * K1g * COUT * 2 +
-           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + 512;
+           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)2 * COUT * 256 + 512;
   }
 };
 
 template <typename T, int COUT, int NMLP>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(448, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
               const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wh,
+              const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
               const MlpArgs<T> args) {
   constexpr int kSlotW = COUT * 3 / 2;
-  constexpr int kQCol = kSlots * kSlotW;   // sum-of-squares accumulators live in TMEM: [kQCol + eg*COUT, +COUT)
-  constexpr uint32_t kTmemCols = (kQCol + 2 * COUT <= 256) ? 256 : 512;
-  static_assert(kQCol + 2 * COUT <= 512, "TMEM budget");
+  constexpr uint32_t kTmemCols = (kSlots * kSlotW <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int K1 = args.K1, K1g = args.K1g, depth = args.depth, Kh = args.Kh;
@@ -315,7 +324,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   uint8_t* s_in = smem;
   uint8_t* s_w1 = s_in + (size_t)kInStages * stage_bytes;      // [2 buffers][NMLP][atoms][COUT][128B]
   uint8_t* s_wh = s_w1 + (size_t)2 * w1_buf_bytes;             // [NMLP][depth-1][atoms][COUT][128B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes);
+  uint8_t* s_out = s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes;   // [2 groups][2 halves][COUT][128 B] swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + (size_t)2 * COUT * 256);
   uint64_t* in_full = bars;                   // [kInStages]
   uint64_t* in_empty = in_full + kInStages;   // [kInStages]
   uint64_t* w1_full = in_empty + kInStages;   // [2]
@@ -323,7 +333,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   uint64_t* wh_full = w1_empty + 2;           // [1]
   uint64_t* mma_done = wh_full + 1;           // [kSlots]
   uint64_t* h_ready = mma_done + kSlots;      // [kSlots]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + kSlots);
+  uint64_t* tile_full = h_ready + kSlots;     // [2] output tile of epilogue group e staged in smem
+  uint64_t* tile_empty = tile_full + 2;       // [2] statistics warps are done with it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 2);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
 
@@ -339,6 +351,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
     mbar_init(wh_full, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&h_ready[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_empty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
@@ -502,77 +515,87 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       }
       TIMING_FLUSH(0, lane == 0);
     }
+  } else if (warp >= 10) {
+    // ================= statistics warps (10-13): sum / sum of squares per channel from the staged tile ==========
+    // thread -> (channel c, part): `part` selects a run of kPxPerPart consecutive pixels of the 128-pixel tile
+    constexpr int kParts = 128 / COUT;             // 2 for COUT = 64, 4 for COUT = 32
+    constexpr int kPxPerPart = 128 / kParts;       // 64 / 32 pixels = 8 / 4 16-byte chunks of one 64-pixel half
+    const int st = threadIdx.x - 320;              // 0..127
+    const int c = st % COUT, part = st / COUT;
+    const int half = (part * kPxPerPart) / 64, chunk0 = ((part * kPxPerPart) % 64) / 8;
+    float acc_s[NMLP], acc_q[NMLP];
+    int acc_g[NMLP];
+#pragma unroll
+    for (int m = 0; m < NMLP; ++m) { acc_s[m] = 0.f; acc_q[m] = 0.f; acc_g[m] = -1; }
+    auto flush = [&](int m) {
+      if (acc_g[m] < 0) return;
+      double* dst = args.stat_acc + (((long)acc_g[m] * NMLP + m) * COUT + c) * 2;
+      atomicAdd(dst, (double)acc_s[m]);
+      atomicAdd(dst + 1, (double)acc_q[m]);
+      acc_s[m] = 0.f;
+      acc_q[m] = 0.f;
+    };
+    Walker w;
+    walker_init(w);
+    uint32_t ph_full = 0;
+    for (long v = 0; v < V; ++v) {
+      const int b = (int)(v & 1);                  // epilogue group (= slot parity) that produced this tile
+      const int m = (int)(v % NMLP);
+      walker_seek(w, t_begin + v / NMLP);
+      const int g = w.g;
+      const int p0 = (int)(t_begin + v / NMLP - w.base) * kTileM;
+#pragma unroll
+      for (int mm = 0; mm < NMLP; ++mm)
+        if (mm == m && g != acc_g[mm]) { flush(mm); acc_g[mm] = g; }
+      mbar_wait(&tile_full[b], (ph_full >> b) & 1u);
+      ph_full ^= 1u << b;
+      const uint8_t* row = s_out + (size_t)b * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
+      float sv = 0.f, qv = 0.f;
+#pragma unroll
+      for (int k = 0; k < kPxPerPart / 8; ++k) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(row + (((chunk0 + k) ^ (c & 7)) << 4));
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = Elem<T>::unpack2(ww[u]);
+          sv += f.x + f.y;
+          qv = fmaf(f.x, f.x, fmaf(f.y, f.y, qv));
+        }
+      }
+      // hole pixels hold a marker (0 or 1), not data: take them out again
+      for (int hp = (geo.BN - 1 - (p0 & (geo.BN - 1))) & (geo.BN - 1); hp < 128; hp += geo.BN) {
+        if (hp >= part * kPxPerPart && hp < (part + 1) * kPxPerPart) {
+          const uint8_t* hrow = s_out + (size_t)b * (COUT * 256) + (size_t)(hp >> 6) * (COUT * 128) + (size_t)c * 128;
+          const uint16_t raw = *reinterpret_cast<const uint16_t*>(hrow + ((((hp & 63) >> 3) ^ (c & 7)) << 4) + (hp & 7) * 2);
+          const float x = Elem<T>::to_float(*reinterpret_cast<const T*>(&raw));
+          sv -= x;
+          qv -= x * x;
+        }
+      }
+#pragma unroll
+      for (int mm = 0; mm < NMLP; ++mm)
+        if (mm == m) { acc_s[mm] += sv; acc_q[mm] += qv; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tile_empty[b]);
+    }
+#pragma unroll
+    for (int mm = 0; mm < NMLP; ++mm) flush(mm);
   } else {
-    // ================= epilogue groups =================
+    // ================= epilogue groups (warps 0-3 / 4-7) =================
     const int eg = warp / 4;                 // 0: slots 0,2   1: slots 1,3
     const int quad = warp % 4;               // TMEM lane quadrant this warp may access
     const int pix_in_tile = quad * 32 + lane;
+    const int et = threadIdx.x - eg * 128;   // thread index inside the group
     uint32_t ph_mma = 0;                     // phase bits of mma_done[s]
-    // per-thread statistics over the pixels this thread has seen: sums in registers, sums of squares in
-    // this thread's TMEM lane (keeps the epilogue inside the 168-register budget of a 10-warp CTA)
-    float acc_s[COUT];
-    const uint32_t q_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kQCol + eg * COUT);
-    {
-      uint32_t z[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) z[u] = 0u;
-#pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 16) tmem_st16(q_addr + (uint32_t)c0, z);
-      tmem_wait_st();
-    }
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) acc_s[c] = 0.f;
-    int acc_g = -1, acc_m = 0;
+    uint32_t ph_te = 0;                      // phase of tile_empty[eg]
     Walker w;
     walker_init(w);
     int slot_g0 = 0, slot_g1 = 0;            // (graph, first tile of graph) of the tile in this group's two slots
     long slot_base0 = 0, slot_base1 = 0;
-
-    // Column sums over the warp's 32 lanes with a transposing butterfly: every stage halves the number of
-    // live values per lane (62 shuffles for 64 channels instead of 320); afterwards lane L holds the
-    // totals of channels {2*rev-ish(L), +1} -- see the index computation in flush_stats.
-    auto warp_reduce64 = [&](float (&v)[COUT]) {
-#pragma unroll
-      for (int half = COUT / 2, o = 16; o >= 1 && half >= 1; half >>= 1, o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-          const float keep = up ? v[i + half] : v[i];
-          const float send = up ? v[i] : v[i + half];
-          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-      }
-    };
-    auto flush_stats = [&]() {
-      double* dst = args.stat_acc + ((long)acc_g * NMLP + acc_m) * COUT * 2;
-      float qv[COUT];
-#pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 16) {
-        uint32_t qq[16];
-        tmem_ld16(q_addr + (uint32_t)c0, qq);
-        tmem_wait_ld();
-#pragma unroll
-        for (int u = 0; u < 16; ++u) { qv[c0 + u] = __uint_as_float(qq[u]); qq[u] = 0u; }
-        tmem_st16(q_addr + (uint32_t)c0, qq);
-      }
-      warp_reduce64(acc_s);
-      warp_reduce64(qv);
-      // after the 5 stages a lane owns COUT/32 consecutive-stride channels: stage with offset o selected
-      // the upper half (of size COUT/2, COUT/4, ...) when (lane & o) != 0
-      constexpr int kLeft = COUT / 32;
-      int cbase = 0;
-#pragma unroll
-      for (int half = COUT / 2, o = 16; o >= 1; half >>= 1, o >>= 1)
-        if (lane & o) cbase += half;
-#pragma unroll
-      for (int i = 0; i < kLeft; ++i) {
-        atomicAdd(dst + 2 * (cbase + i), (double)acc_s[i]);
-        atomicAdd(dst + 2 * (cbase + i) + 1, (double)qv[i]);
-      }
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) acc_s[c] = 0.f;
-      tmem_wait_st();
-    };
+    // staged output tile of this group: [half][COUT rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+    uint8_t* tile = s_out + (size_t)eg * (COUT * 256);
+    uint8_t* my_half = tile + (size_t)(pix_in_tile >> 6) * (COUT * 128) + (pix_in_tile & 7) * 2;
+    const int my_chunk = (pix_in_tile & 63) >> 3;
 
     TIMING_DECL;
     for (long v0 = 0; v0 < V; v0 += kSlots) {
@@ -622,9 +645,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             }
             tmem_wait_st();
             TIMING_MARK(2);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_ready[s]);
           } else {
-            acc_g = g;
-            acc_m = m;
             const int n = graph_n(args.n_per_graph, g, geo.N);
             // pixel coordinates with 32-bit arithmetic: one division per tile, then at most two row wraps
             const int p0 = (int)(t_begin + seq - gbase) * kTileM;
@@ -632,83 +656,64 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             int pj = p0 - pi * geo.NPC + pix_in_tile;
             if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
             if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
-            const int p = p0 + pix_in_tile;
             const bool in_plane = pi < geo.N;
             const bool hole = (pj & (geo.BN - 1)) == geo.BN - 1;
             const int j = pj - (pj >> geo.BNLOG);
             const bool valid = in_plane && !hole && pi < n && j < n;
-            // main element and (optionally) the ones row/column element this thread is responsible for
-            long off_main = -1, off_ones = -1;
-            float hole_val = 0.f, ones_val = 0.f;
-            long plane_stride;
-            if (args.out_mode[m] == kOutC) {
-              plane_stride = geo.PSC;
-              if (in_plane) off_main = p;                 // holes are written too (ones or zero)
-              if (hole) hole_val = (args.ones[m] && pi < n) ? 1.f : 0.f;
-            } else {
-              plane_stride = geo.PSA;
-              if (in_plane && !hole && j < geo.N) {
-                const int mt = pi / kTM1;
-                off_main = (long)(pi + mt) * geo.NPA + j;
-                if (args.ones[m] && pi < n && (pi - mt * kTM1 == kTM1 - 1 || pi == n - 1)) {
-                  off_ones = (long)(mt * 128 + 127) * geo.NPA + j;
-                  ones_val = (j < n) ? 1.f : 0.f;
-                }
-              }
-            }
-            T* obase = args.out[m] + (long)g * COUT * plane_stride;
-            T* optr = obase + (off_main >= 0 ? off_main : 0);
-            const bool do_store = off_main >= 0;
+            const int mode = args.out_mode[m];
+            // holes of Y2 (layout B) hold ones on valid rows: they are the matmul's ones column
+            const float marker = (hole && mode == kOutB && args.ones[m] && pi < n) ? 1.f : 0.f;
+            // the staging buffer is free once the previous TMA store has read it and the statistics warps are done
+            if (et == 0) bulk_wait_group_read0();
+            mbar_wait(&tile_empty[eg], ph_te ^ 1u);
+            ph_te ^= 1u;
+            named_bar_sync(1 + eg, 128);
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 16) {
-              uint32_t r[16], qq[16];
-              tmem_ld16(lane_addr + (uint32_t)c0, r);
-              tmem_ld16(q_addr + (uint32_t)c0, qq);
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+              uint32_t r[32];
+              tmem_ld32(lane_addr + (uint32_t)c0, r);
               tmem_wait_ld();
 #pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                const float x = valid ? __uint_as_float(r[u]) : 0.f;
-                acc_s[c0 + u] += x;
-                qq[u] = __float_as_uint(fmaf(x, x, __uint_as_float(qq[u])));
-                r[u] = __float_as_uint(x + hole_val);     // x == 0 in holes: the stored value is the ones/zero marker
+              for (int u = 0; u < 32; ++u) {
+                const int c = c0 + u;
+                const float x = (valid ? __uint_as_float(r[u]) : 0.f) + marker;
+                *reinterpret_cast<uint16_t*>(my_half + c * 128 + ((my_chunk ^ (c & 7)) << 4)) = Elem<T>::bits(x);
               }
-              tmem_st16(q_addr + (uint32_t)c0, qq);
-              if (do_store) {
+            }
+            // accumulator drained: the MMA warp may reuse the slot while the tile is being stored
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_ready[s]);
+            fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
+            named_bar_sync(1 + eg, 128);
+            if (et == 0) {
+              const CUtensorMap* mo = (m == 0) ? &map_o0 : &map_o1;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                  *optr = Elem<T>::from_float(__uint_as_float(r[u]));
-                  optr += plane_stride;
-                }
+              for (int hf = 0; hf < 2; ++hf) {
+                const int ph = p0 + hf * 64;                 // a 64-pixel half never straddles a row (NPC % 64 == 0)
+                const int row = ph / geo.NPC, col = ph - row * geo.NPC;
+                const int prow = (mode == kOutA) ? row + row / kTM1 : (mode == kOutB ? row + row / geo.TN1 : row);
+                if (row < geo.N) tma_store_3d(mo, tile + (size_t)hf * (COUT * 128), col, prow, g * COUT);
+              }
+              bulk_commit_group();
+              mbar_arrive(&tile_full[eg]);
+            }
+            // ones rows of Y1 (layout A): the last logical row of every 127-row matmul tile writes the row below it
+            if (mode == kOutA && args.ones[m] && in_plane && pi < n) {
+              const int mt = pi / kTM1;
+              if (pi - mt * kTM1 == kTM1 - 1 || pi == n - 1) {
+                T* o1 = args.out[m] + (long)g * COUT * geo.PSA + (long)(mt * 128 + 127) * geo.NPC + pj;
+                const T ov = Elem<T>::from_float((!hole && j < n) ? 1.f : 0.f);
+                for (int c = 0; c < COUT; ++c) o1[(long)c * geo.PSA] = ov;
               }
             }
-            if (off_ones >= 0) {                          // rare: last logical row of a 127-row matmul tile
-              T* o1 = obase + off_ones;
-              const T ov = Elem<T>::from_float(ones_val);
-              for (int c = 0; c < COUT; ++c) o1[(long)c * plane_stride] = ov;
-            }
-            tmem_wait_st();
-            // flush the per-thread statistics when the next tile this group finishes belongs to another
-            // (graph, MLP) or does not exist -- the only call site of the (large) reduction code
-            {
-              const long vn = (s + 2 < kSlots && v0 + s + 2 < V) ? (v + 2) : (v0 + kSlots + eg);
-              bool flush = vn >= V;
-              if (!flush) {
-                Walker w2 = w;
-                walker_seek(w2, t_begin + vn / NMLP);
-                flush = (w2.g != g) || ((int)(vn % NMLP) != m);
-              }
-              TIMING_MARK(3);
-              if (flush) flush_stats();
-              TIMING_MARK(4);
-            }
+            TIMING_MARK(3);
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&h_ready[s]);
           TIMING_MARK(5);
         }
       }
     }
+    if (et == 0) bulk_wait_group0();           // all TMA stores of this group have landed before the CTA exits
     TIMING_FLUSH(8, warp == 2 && lane == 0);
   }
   tc_fence_before();
@@ -829,7 +834,7 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (long t = blockIdx.x; t < total; t += gridDim.x) {
         int q, m, nn, n;
         tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
-        const int kts = (n + 63) / 64;
+        const int kts = (phys_k_end(n, geo.TN1) + 63) / 64;     // K runs over PHYSICAL columns of Y1 / rows of Y2
         for (int kt = 0; kt < kts; ++kt) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
@@ -859,7 +864,7 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (long t = blockIdx.x; t < total; t += gridDim.x) {
         int q, m, nn, n;
         tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
-        const int kts = (n + 63) / 64;
+        const int kts = (phys_k_end(n, geo.TN1) + 63) / 64;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -978,12 +983,12 @@ EncodeFn get_encode() {
 
 // 3-D tensor map over 16-bit data: dims (d0 contiguous, d1, d2), strides in elements, 128B swizzle.
 int make_map3(CUtensorMap* m, int fmt_is_bf16, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-              uint64_t stride1_elems, uint64_t stride2_elems, uint32_t b0, uint32_t b1) {
+              uint64_t stride1_elems, uint64_t stride2_elems, uint32_t b0, uint32_t b1, uint32_t b2 = 1) {
   EncodeFn enc = get_encode();
   if (!enc) return fail(FGNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
-  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15))
     return fail(FGNN_ERR_INVALID, "tensor map alignment: base %p strides %llu %llu", base,
@@ -1021,9 +1026,9 @@ int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const f
   constexpr int is_bf16 = Elem<T>::kFmt;
   CUtensorMap ma, mb;
   const uint64_t planes = (uint64_t)G * C;
-  // A: columns beyond N are out of bounds (zero filled) so stale pitch padding never reaches the MMA
-  if (int e = make_map3(&ma, is_bf16, y1, geo.N, geo.PRA, planes, geo.NPA, (uint64_t)geo.PSA, 64, 128)) return e;
-  if (int e = make_map3(&mb, is_bf16, y2, geo.NPC, geo.N, planes, geo.NPC, (uint64_t)geo.PSC, 64, 64)) return e;
+  // K = physical column of Y1 (layout A) = physical row of Y2 (layout B); reads past either extent are zero filled
+  if (int e = make_map3(&ma, is_bf16, y1, geo.NPC, geo.PRA, planes, geo.NPC, (uint64_t)geo.PSA, 64, 128)) return e;
+  if (int e = make_map3(&mb, is_bf16, y2, geo.NPC, geo.PRB, planes, geo.NPC, (uint64_t)geo.PSB, 64, 64)) return e;
   MatmulArgs<T> a{G, C, geo, out, coef_a, coef_b, npg};
   const int grid = num_sms();
 #define FGNN_MM_LAUNCH(BNV)                                                                              \
@@ -1086,7 +1091,13 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   a.stat_acc = L.stat_acc;
   a.n_per_graph = npg;
   FGNN_CHECK_ARG(a.K1 <= 256, "first-layer K=%d too wide for the tensor-core MLP kernel", a.K1);
-  CUtensorMap mx0, mx1, mw1, mwh;
+  CUtensorMap mx0, mx1, mw1, mwh, mo[2];
+  for (int m = 0; m < NMLP; ++m) {
+    const int rows = L.out_mode[m] == kOutA ? geo.PRA : (L.out_mode[m] == kOutB ? geo.PRB : geo.N);
+    if (int e = make_map3(&mo[m], is_bf16, L.out[m], geo.NPC, rows, (uint64_t)G * COUT, geo.NPC, (uint64_t)rows * geo.NPC,
+                          64, 1, COUT)) return e;
+  }
+  if (NMLP == 1) mo[1] = mo[0];
   if (int e = make_map3(&mx0, is_bf16, L.src[0], geo.PSC, L.c_src[0], G, geo.PSC, (uint64_t)L.c_src[0] * geo.PSC, 64, a.k_src[0])) return e;
   if (L.nsrc > 1) {
     if (int e = make_map3(&mx1, is_bf16, L.src[1], geo.PSC, L.c_src[1], G, geo.PSC, (uint64_t)L.c_src[1] * geo.PSC, 64, a.k_src[1])) return e;
@@ -1111,7 +1122,7 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   int grid = (int)std::min<long>((long)num_sms(), total_tiles);
   if (grid < 1) grid = 1;
   prof::begin(prof::kMlp, st);
-  tc_mlp_kernel<T, COUT, NMLP><<<grid, 320, smem, st>>>(mx0, mx1, mw1, mwh, a);
+  tc_mlp_kernel<T, COUT, NMLP><<<grid, 448, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
   prof::end(prof::kMlp, st);
   FGNN_LAUNCHED();
   return FGNN_OK;
@@ -1233,7 +1244,7 @@ int make_plan(const fgnn_embed_params& p, int G, int N, Plan& pl) {
     return fail(FGNN_ERR_UNSUPPORTED, "tensor-core path supports in/out_features 32 or 64 (got %d); use FGNN_FP32", pl.C);
   if (pl.cin0 > 64) return fail(FGNN_ERR_UNSUPPORTED, "original_features_num %d > 64 unsupported", pl.cin0);
   const int chunk_env = env_int("FGNN_TC_CHUNK", 0);
-  long per_graph = ((long)(4 * pl.C + pl.cin0) * pl.geo.PSC + (long)pl.C * pl.geo.PSA) * 2;
+  long per_graph = ((long)(3 * pl.C + pl.cin0) * pl.geo.PSC + (long)pl.C * (pl.geo.PSA + pl.geo.PSB)) * 2;
   long budget = (long)6 << 30;
   long chunk = chunk_env > 0 ? chunk_env : std::max<long>(1, budget / std::max<long>(per_graph, 1));
   chunk = std::min<long>(chunk, 65535 / std::max(pl.C, pl.cin0));   // grid.y limits of the helper kernels
@@ -1256,7 +1267,7 @@ size_t carve(const Plan& pl, int num_blocks, Arena& ar, Buffers& B) {
   B.xa = ar.take<uint16_t>(actC, 1024);
   B.xb = ar.take<uint16_t>(actC, 1024);
   B.y1 = ar.take<uint16_t>((size_t)pl.chunk * pl.C * pl.geo.PSA, 1024);
-  B.y2 = ar.take<uint16_t>(actC, 1024);
+  B.y2 = ar.take<uint16_t>((size_t)pl.chunk * pl.C * pl.geo.PSB, 1024);
   B.mult = ar.take<uint16_t>(actC, 1024);
   const size_t nc = (size_t)pl.chunk * pl.C;
   B.coef1 = ar.take<float>(nc * 2);
@@ -1308,6 +1319,11 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, i
                                                 geo, 0, n_c);
       FGNN_LAUNCHED();
     }
+    {
+      dim3 grid(4, gc * C);
+      zero_hole_rows_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<T*>(B.y2), geo);
+      FGNN_LAUNCHED();
+    }
     const T* cur = reinterpret_cast<const T*>(B.xin);
     int cur_c = pl.cin0;
     const float* cur_coef = nullptr;
@@ -1327,7 +1343,7 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, i
         M.wf = reinterpret_cast<T*>(B.wf12); M.bf = B.bf12;
         M.wh = whb;
         M.out[0] = y1; M.out_mode[0] = kOutA; M.ones[0] = 1; M.coef[0] = B.coef1;
-        M.out[1] = y2; M.out_mode[1] = kOutC; M.ones[1] = 1; M.coef[1] = B.coef2;
+        M.out[1] = y2; M.out_mode[1] = kOutB; M.ones[1] = 1; M.coef[1] = B.coef2;
         M.stat_acc = B.stat_acc;
         if (int e = run_mlp_group<T>(M, C, gc, geo, n_c, st)) return e;
       }
@@ -1380,7 +1396,7 @@ int embed_fwd(const fgnn_embed_params& p, int precision, const float* x, float* 
 // ---- debug: one tensor-core matmul on fp32 host-layout tensors ---------------------------------
 size_t debug_matmul_workspace_bytes(int G, int C, int N) {
   Geo geo = make_geo(N);
-  return align_up(((size_t)2 * G * C * geo.PSC + (size_t)G * C * geo.PSA) * 2 + 8192, 1024);
+  return align_up(((size_t)G * C * (geo.PSC + geo.PSA + geo.PSB)) * 2 + 8192, 1024);
 }
 
 template <typename T>
@@ -1390,13 +1406,14 @@ int debug_matmul_t(const float* a, const float* b, float* out, int G, int C, int
   if (ws_bytes < debug_matmul_workspace_bytes(G, C, N)) return fail(FGNN_ERR_WORKSPACE, "debug workspace too small");
   Arena ar(ws, ws_bytes);
   T* y1 = ar.take<T>((size_t)G * C * geo.PSA, 1024);
-  T* y2 = ar.take<T>((size_t)G * C * geo.PSC, 1024);
+  T* y2 = ar.take<T>((size_t)G * C * geo.PSB, 1024);
   T* mo = ar.take<T>((size_t)G * C * geo.PSC, 1024);
   dim3 gridA((unsigned)std::min<long>(64, (geo.PSA + 255) / 256), G * C);
   dim3 gridC((unsigned)std::min<long>(64, (geo.PSC + 255) / 256), G * C);
   to_planes_kernel<T><<<gridA, 256, 0, st>>>(a, y1, C, geo, 1, npg);
   FGNN_LAUNCHED();
-  to_planes_kernel<T><<<gridC, 256, 0, st>>>(b, y2, C, geo, 0, npg);
+  dim3 gridB((unsigned)std::min<long>(64, (geo.PSB + 255) / 256), G * C);
+  to_planes_kernel<T><<<gridB, 256, 0, st>>>(b, y2, C, geo, 2, npg);
   FGNN_LAUNCHED();
   FGNN_CUDA(cudaMemsetAsync(mo, 0, (size_t)G * C * geo.PSC * sizeof(T), st));
   if (int e = launch_matmul<T>(y1, y2, mo, nullptr, nullptr, G, C, geo, npg, st)) return e;
