@@ -56,7 +56,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) 
         : "=r"(ok)
         : "r"(bar_addr), "r"(parity)
         : "memory");
-    if (!ok) __nanosleep(32);  // back off: pollers must not steal issue slots from the single MMA-issuing lane
+    // (no software back-off: try_wait already suspends the warp in hardware and wake-up latency is on the critical path)
     if (!ok && clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       printf("fgnn: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              bar_addr, parity);
