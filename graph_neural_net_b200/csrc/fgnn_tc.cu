@@ -295,13 +295,14 @@ __device__ unsigned long long g_tc_timing[16];
 #define TIMING_MARK(slot)
 #define TIMING_FLUSH(base, cond)
 #endif
-constexpr int kInStages = 4;
+constexpr int kMaxInStages = 4;
+__host__ __device__ inline int mlp_in_stages(int K1) { return K1 >= 128 ? 3 : 4; }   // 32 KB stages at K1 = 128
 
 template <int COUT, int NMLP>
 struct MlpSmem {
   static size_t bytes(int K1, int K1g, int depth, int Kh) {
-    return 1024 + (size_t)kInStages * K1 * 256 + (size_t)2 * NMLP * K1g * COUT * 2 +
-           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)2 * COUT * 256 + 512;
+    return 1024 + (size_t)mlp_in_stages(K1) * K1 * 256 + (size_t)2 * NMLP * K1g * COUT * 2 +
+           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)4 * COUT * 256 + 512;
   }
 };
 
@@ -318,24 +319,25 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   const int K1 = args.K1, K1g = args.K1g, depth = args.depth, Kh = args.Kh;
   const Geo geo = args.geo;
   const uint32_t stage_bytes = (uint32_t)K1 * 256u;
+  const int kInStages = mlp_in_stages(K1);
   const uint32_t w1_mlp_bytes = (uint32_t)K1g * COUT * 2u;     // one MLP's folded first-layer weights
   const uint32_t w1_buf_bytes = w1_mlp_bytes * NMLP;           // one graph's
   const uint32_t wh_mat_bytes = (uint32_t)Kh * COUT * 2u;
   uint8_t* s_in = smem;
   uint8_t* s_w1 = s_in + (size_t)kInStages * stage_bytes;      // [2 buffers][NMLP][atoms][COUT][128B]
   uint8_t* s_wh = s_w1 + (size_t)2 * w1_buf_bytes;             // [NMLP][depth-1][atoms][COUT][128B]
-  uint8_t* s_out = s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes;   // [2 groups][2 halves][COUT][128 B] swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + (size_t)2 * COUT * 256);
-  uint64_t* in_full = bars;                   // [kInStages]
-  uint64_t* in_empty = in_full + kInStages;   // [kInStages]
-  uint64_t* w1_full = in_empty + kInStages;   // [2]
+  uint8_t* s_out = s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes;   // [2 groups][2 buffers][2 halves][COUT][128 B] swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + (size_t)4 * COUT * 256);
+  uint64_t* in_full = bars;                      // [kInStages]
+  uint64_t* in_empty = in_full + kMaxInStages;   // [kInStages]
+  uint64_t* w1_full = in_empty + kMaxInStages;   // [2]
   uint64_t* w1_empty = w1_full + 2;           // [2]
   uint64_t* wh_full = w1_empty + 2;           // [1]
   uint64_t* mma_done = wh_full + 1;           // [kSlots]
   uint64_t* h_ready = mma_done + kSlots;      // [kSlots]
-  uint64_t* tile_full = h_ready + kSlots;     // [2] output tile of epilogue group e staged in smem
-  uint64_t* tile_empty = tile_full + 2;       // [2] statistics warps are done with it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 2);
+  uint64_t* tile_full = h_ready + kSlots;     // [2 groups][2 buffers] output tile staged in smem
+  uint64_t* tile_empty = tile_full + 4;       // [2][2] statistics warps are done with it AND its TMA store has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 4);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
 
@@ -351,7 +353,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
     mbar_init(wh_full, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&h_ready[s], 4); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_empty[s], 4); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_empty[s], 5); }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
@@ -537,9 +539,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     };
     Walker w;
     walker_init(w);
-    uint32_t ph_full = 0;
+    int items[2] = {0, 0};                         // final items consumed per epilogue group
     for (long v = 0; v < V; ++v) {
       const int b = (int)(v & 1);                  // epilogue group (= slot parity) that produced this tile
+      const int kb = (b == 0) ? items[0]++ : items[1]++;
+      const int buf = b * 2 + (kb & 1);
       const int m = (int)(v % NMLP);
       walker_seek(w, t_begin + v / NMLP);
       const int g = w.g;
@@ -547,9 +551,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
 #pragma unroll
       for (int mm = 0; mm < NMLP; ++mm)
         if (mm == m && g != acc_g[mm]) { flush(mm); acc_g[mm] = g; }
-      mbar_wait(&tile_full[b], (ph_full >> b) & 1u);
-      ph_full ^= 1u << b;
-      const uint8_t* row = s_out + (size_t)b * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
+      mbar_wait(&tile_full[buf], (uint32_t)(kb >> 1) & 1u);
+      const uint8_t* row = s_out + (size_t)buf * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
       float sv = 0.f, qv = 0.f;
 #pragma unroll
       for (int k = 0; k < kPxPerPart / 8; ++k) {
@@ -565,7 +568,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       // hole pixels hold a marker (0 or 1), not data: take them out again
       for (int hp = (geo.BN - 1 - (p0 & (geo.BN - 1))) & (geo.BN - 1); hp < 128; hp += geo.BN) {
         if (hp >= part * kPxPerPart && hp < (part + 1) * kPxPerPart) {
-          const uint8_t* hrow = s_out + (size_t)b * (COUT * 256) + (size_t)(hp >> 6) * (COUT * 128) + (size_t)c * 128;
+          const uint8_t* hrow = s_out + (size_t)buf * (COUT * 256) + (size_t)(hp >> 6) * (COUT * 128) + (size_t)c * 128;
           const uint16_t raw = *reinterpret_cast<const uint16_t*>(hrow + ((((hp & 63) >> 3) ^ (c & 7)) << 4) + (hp & 7) * 2);
           const float x = Elem<T>::to_float(*reinterpret_cast<const T*>(&raw));
           sv -= x;
@@ -576,7 +579,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       for (int mm = 0; mm < NMLP; ++mm)
         if (mm == m) { acc_s[mm] += sv; acc_q[mm] += qv; }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tile_empty[b]);
+      if (lane == 0) mbar_arrive(&tile_empty[buf]);
     }
 #pragma unroll
     for (int mm = 0; mm < NMLP; ++mm) flush(mm);
@@ -587,14 +590,13 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     const int pix_in_tile = quad * 32 + lane;
     const int et = threadIdx.x - eg * 128;   // thread index inside the group
     uint32_t ph_mma = 0;                     // phase bits of mma_done[s]
-    uint32_t ph_te = 0;                      // phase of tile_empty[eg]
+    int n_final = 0;                         // final-layer items this group has produced (staging buffer = n_final & 1)
     Walker w;
     walker_init(w);
     int slot_g0 = 0, slot_g1 = 0;            // (graph, first tile of graph) of the tile in this group's two slots
     long slot_base0 = 0, slot_base1 = 0;
-    // staged output tile of this group: [half][COUT rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
-    uint8_t* tile = s_out + (size_t)eg * (COUT * 256);
-    uint8_t* my_half = tile + (size_t)(pix_in_tile >> 6) * (COUT * 128) + (pix_in_tile & 7) * 2;
+    // staged output tiles of this group: 2 buffers x [half][COUT rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+    const size_t my_off = (size_t)(pix_in_tile >> 6) * (COUT * 128) + (pix_in_tile & 7) * 2;
     const int my_chunk = (pix_in_tile & 63) >> 3;
 
     TIMING_DECL;
@@ -663,11 +665,12 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             const int mode = args.out_mode[m];
             // holes of Y2 (layout B) hold ones on valid rows: they are the matmul's ones column
             const float marker = (hole && mode == kOutB && args.ones[m] && pi < n) ? 1.f : 0.f;
-            // the staging buffer is free once the previous TMA store has read it and the statistics warps are done
-            if (et == 0) bulk_wait_group_read0();
-            mbar_wait(&tile_empty[eg], ph_te ^ 1u);
-            ph_te ^= 1u;
-            named_bar_sync(1 + eg, 128);
+            // staging buffer: free once the statistics warps have read its previous tile and that tile's TMA store
+            // has read it too (thread 0 of the group arrives for the store, see below)
+            const int buf = eg * 2 + (n_final & 1);
+            uint8_t* tile = s_out + (size_t)buf * (COUT * 256);
+            uint8_t* my_half = tile + my_off;
+            mbar_wait(&tile_empty[buf], ((uint32_t)(n_final >> 1) & 1u) ^ 1u);
 #pragma unroll
             for (int c0 = 0; c0 < COUT; c0 += 32) {
               uint32_t r[32];
@@ -696,8 +699,12 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
                 if (row < geo.N) tma_store_3d(mo, tile + (size_t)hf * (COUT * 128), col, prow, g * COUT);
               }
               bulk_commit_group();
-              mbar_arrive(&tile_full[eg]);
+              mbar_arrive(&tile_full[buf]);
+              // the store issued one final item ago has finished reading the OTHER buffer -> hand it back
+              bulk_wait_group_read1();
+              if (n_final >= 1) mbar_arrive(&tile_empty[buf ^ 1]);
             }
+            ++n_final;
             // ones rows of Y1 (layout A): the last logical row of every 127-row matmul tile writes the row below it
             if (mode == kOutA && args.ones[m] && in_plane && pi < n) {
               const int mt = pi / kTM1;
