@@ -261,7 +261,8 @@ pool_kernel(const T* __restrict__ y, const float* __restrict__ coef, float* __re
 //   layer>=2: D = relu(D + b) (16-bit, written back to TMEM) * W^T        A = TMEM, B = smem
 //   output: raw last-layer accumulators as 16-bit planes (the last bias cancels in GraphNorm), their
 //           per-(graph, channel) sum and sum of squares (fp32 in registers, double atomics per flush).
-// Warp roles: warps 0-3 / 4-7 two epilogue groups, warp 8 TMA producer, warp 9 MMA issuer; the groups
+// Warp roles: warps 0-3 / 4-7 two epilogue groups, warp 8 TMA producer, warps 9-10 MMA issuers (one per group),
+// warps 11-14 GraphNorm statistics; the groups
 // alternate virtual tiles (slot parity).  TMEM slot s: accumulator columns [s*1.5*COUT, +COUT),
 // packed hidden activations in the next COUT/2 columns.
 // =============================================================================================
@@ -307,7 +308,7 @@ struct MlpSmem {
 };
 
 template <typename T, int COUT, int NMLP>
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(480, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
               const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wh,
               const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
@@ -349,8 +350,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   const long V = (t_end - t_begin) * NMLP;  // virtual tiles of this CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kInStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
+    for (int s = 0; s < kInStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], NMLP); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 2); }
     mbar_init(wh_full, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&h_ready[s], 4); }
     for (int s = 0; s < 4; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_empty[s], 5); }
@@ -430,99 +431,91 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 9 || warp == 10) {
+    // ================= MMA issuers: one warp per epilogue group (whole warp, elected lane issues) =================
+    // Warp 9+e feeds the two TMEM slots of group e in that group's own item order, so a slow group never
+    // blocks the other one and each issuer handles half of the tcgen05 traffic.
+    const int eg = warp - 9;
     if (V > 0) {
-      // ================= MMA issuer (whole warp, elected lane issues) =================
-      const uint32_t idesc1 = make_idesc(Elem<T>::kFmt, /*A MN-major*/ 1, /*B K-major*/ 0, kTileM, COUT);
-      const uint32_t idesc2 = make_idesc(Elem<T>::kFmt, 0, 0, kTileM, COUT);
-      Walker w;
-      walker_init(w);
-      int cur_g = -1, nchg = 0, wbuf = 0;
-      uint32_t ph_w1f = 0, ph_inf = 0, ph_h = 0;   // phase bits, one per barrier (kept in registers)
-      // descriptor templates: only the 14-bit start-address field (bits 0-13, units of 16 B) varies per MMA
-      const uint64_t a_d0 = smem_desc_sw128(smem_u32(s_in), (uint32_t)K1 * 128u, 1024u);   // MN-major activations
-      const uint64_t b_d0 = smem_desc_sw128(smem_u32(s_w1), 16u, 1024u);                   // K-major weights
-      const uint32_t a_desc_lo0 = (uint32_t)a_d0, a_desc_hi = (uint32_t)(a_d0 >> 32);
-      const uint32_t w1_desc_lo0 = (uint32_t)b_d0, b_desc_hi = (uint32_t)(b_d0 >> 32);
-      const uint32_t wh_desc_lo0 = (uint32_t)smem_desc_sw128(smem_u32(s_wh), 16u, 1024u);
+    const uint32_t idesc1 = make_idesc(Elem<T>::kFmt, /*A MN-major*/ 1, /*B K-major*/ 0, kTileM, COUT);
+    const uint32_t idesc2 = make_idesc(Elem<T>::kFmt, 0, 0, kTileM, COUT);
+    const uint64_t a_d0 = smem_desc_sw128(smem_u32(s_in), (uint32_t)K1 * 128u, 1024u);   // MN-major activations
+    const uint64_t b_d0 = smem_desc_sw128(smem_u32(s_w1), 16u, 1024u);                   // K-major weights
+    const uint32_t a_desc_lo0 = (uint32_t)a_d0, a_desc_hi = (uint32_t)(a_d0 >> 32);
+    const uint32_t w1_desc_lo0 = (uint32_t)b_d0, b_desc_hi = (uint32_t)(b_d0 >> 32);
+    const uint32_t wh_desc_lo0 = (uint32_t)smem_desc_sw128(smem_u32(s_wh), 16u, 1024u);
+    Walker wi;                               // walker of the issue path (layer-1 issues run ahead of the epilogue)
+    walker_init(wi);
+    walker_seek(wi, t_begin);
+    const int g_first = wi.g;
+    int issue_gidx = 0;                      // graphs (relative to g_first) whose weight buffer this group has released
+    auto release_graphs_upto = [&](int gidx) {   // all MMAs of this group that read buffers of graphs < gidx were issued
+      for (; issue_gidx < gidx; ++issue_gidx) mma_commit_e(&w1_empty[issue_gidx & 1]);
+    };
+    auto issue_layer1 = [&](long v, int s) {     // first conv of virtual tile v into slot s
+      const long seq = v / NMLP;
+      const int m = (int)(v % NMLP);
+      const int st = (int)(seq % kInStages);
+      walker_seek(wi, t_begin + seq);
+      const int gidx = wi.g - g_first;
+      if (gidx > issue_gidx) release_graphs_upto(gidx);
+      const int wbuf = gidx & 1;
+      mbar_wait(&w1_full[wbuf], (uint32_t)(gidx >> 1) & 1u);
+      mbar_wait(&in_full[st], (uint32_t)(seq / kInStages) & 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
+      uint32_t a_lo = a_desc_lo0 + (uint32_t)st * (stage_bytes >> 4);
+      uint32_t b_lo = w1_desc_lo0 + (((uint32_t)wbuf * w1_buf_bytes + (uint32_t)m * w1_mlp_bytes) >> 4);
+      const int ksteps = K1 / 16;
+#pragma unroll 1
+      for (int k = 0; k < ksteps; ++k) {
+        mma_ss2_e(d_tmem, a_lo, a_desc_hi, b_lo, b_desc_hi, idesc1, k > 0 ? 1u : 0u);
+        a_lo += 2048u >> 4;                                       // next 16 K-rows of the MN-major tile
+        b_lo += ((k & 3) == 3) ? ((COUT * 128u - 96u) >> 4) : (32u >> 4);  // next K atom / next 32 B
+      }
+      mma_commit_e(&in_empty[st]);             // NMLP arrivals free the input stage
+      mma_commit_e(&mma_done[s]);
+    };
+    auto issue_hidden = [&](int s, int m, int l) {   // layer l >= 1 of the tile in slot s: A = packed activations in TMEM
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
+      const uint32_t wl_lo = wh_desc_lo0 + (uint32_t)(m * (depth - 1) + (l - 1)) * (wh_mat_bytes >> 4);
+#pragma unroll
+      for (int k = 0; k < COUT / 16; ++k)
+        mma_ts2_e(d_tmem, d_tmem + COUT + (uint32_t)k * 8u,
+                  wl_lo + (((uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u) >> 4), b_desc_hi, idesc2,
+                  k > 0 ? 1u : 0u);
+      mma_commit_e(&mma_done[s]);
+    };
       if (depth > 1) mbar_wait(wh_full, 0);
-      TIMING_DECL;
+      for (int s = eg; s < kSlots; s += 2)     // prime both slots with the first wave
+        if (s < V) issue_layer1(s, s);
+      uint32_t ph_h = 0;                       // phase bits of h_ready[s]
       for (long v0 = 0; v0 < V; v0 += kSlots) {
 #pragma unroll 1
         for (int l = 0; l < depth; ++l) {
 #pragma unroll 1
-          for (int s = 0; s < kSlots; ++s) {
+          for (int s = eg; s < kSlots; s += 2) {
             const long v = v0 + s;
             if (v >= V) break;
-            const long seq = v / NMLP;
             const int m = (int)(v % NMLP);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
-            TIMING_MARK(0);
-            if (l == 0) {
-              const int st = (int)(seq % kInStages);
-              if (m == 0) {
-                walker_seek(w, t_begin + seq);
-                if (w.g != cur_g) {
-                  if (cur_g >= 0) mma_commit_e(&w1_empty[wbuf]);  // all MMAs that read the old buffer retire first
-                  wbuf = nchg & 1;
-                  mbar_wait(&w1_full[wbuf], (ph_w1f >> wbuf) & 1u);
-                  ph_w1f ^= 1u << wbuf;
-                  cur_g = w.g;
-                  ++nchg;
-                }
-                mbar_wait(&in_full[st], (ph_inf >> st) & 1u);
-                ph_inf ^= 1u << st;
-              }
-              TIMING_MARK(1);
-              if (v >= kSlots) {  // slot reuse: previous occupant's accumulator must be drained
-                mbar_wait(&h_ready[s], (ph_h >> s) & 1u);
-                ph_h ^= 1u << s;
-              }
-              TIMING_MARK(2);
-              tc_fence_after();
-              {
-                uint32_t a_lo = a_desc_lo0 + (uint32_t)st * (stage_bytes >> 4);
-                uint32_t b_lo = w1_desc_lo0 + ((uint32_t)wbuf * w1_buf_bytes + (uint32_t)m * w1_mlp_bytes >> 4);
-                const int ksteps = K1 / 16;
-#pragma unroll 1
-                for (int k = 0; k < ksteps; ++k) {
-                  mma_ss2_e(d_tmem, a_lo, a_desc_hi, b_lo, b_desc_hi, idesc1, k > 0 ? 1u : 0u);
-                  a_lo += 2048u >> 4;                                       // next 16 K-rows of the MN-major tile
-                  b_lo += ((k & 3) == 3) ? ((COUT * 128u - 96u) >> 4) : (32u >> 4);  // next K atom / next 32 B
-                }
-              }
-              if (m == NMLP - 1) mma_commit_e(&in_empty[st]);
-              mma_commit_e(&mma_done[s]);
-              TIMING_MARK(3);
-            } else {
-              mbar_wait(&h_ready[s], (ph_h >> s) & 1u);
-              ph_h ^= 1u << s;
-              TIMING_MARK(2);
-              tc_fence_after();
-              TIMING_MARK(3);
-              {
-                const uint32_t wl_lo = wh_desc_lo0 + (uint32_t)(m * (depth - 1) + (l - 1)) * (wh_mat_bytes >> 4);
-#pragma unroll
-                for (int k = 0; k < COUT / 16; ++k)
-                  mma_ts2_e(d_tmem, d_tmem + COUT + (uint32_t)k * 8u,
-                          wl_lo + (((uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u) >> 4), b_desc_hi, idesc2,
-                          k > 0 ? 1u : 0u);
-              }
-              TIMING_MARK(4);
-              mma_commit_e(&mma_done[s]);
-              TIMING_MARK(5);
-            }
+            mbar_wait(&h_ready[s], (ph_h >> s) & 1u);   // epilogue of (v, l) done: operand written / accumulator drained
+            ph_h ^= 1u << s;
+            if (l < depth - 1) issue_hidden(s, m, l + 1);
+            else if (v + kSlots < V) issue_layer1(v + kSlots, s);
           }
         }
       }
-      TIMING_FLUSH(0, lane == 0);
+      Walker wl = wi;                          // the producer may still wait for this group's release of later graphs
+      walker_seek(wl, t_end - 1);
+      release_graphs_upto(wl.g - g_first + 1);
     }
-  } else if (warp >= 10) {
-    // ================= statistics warps (10-13): sum / sum of squares per channel from the staged tile ==========
+  } else if (warp >= 11) {
+    // ================= statistics warps (11-14): sum / sum of squares per channel from the staged tile ==========
     // thread -> (channel c, part): `part` selects a run of kPxPerPart consecutive pixels of the 128-pixel tile
     constexpr int kParts = 128 / COUT;             // 2 for COUT = 64, 4 for COUT = 32
     constexpr int kPxPerPart = 128 / kParts;       // 64 / 32 pixels = 8 / 4 16-byte chunks of one 64-pixel half
-    const int st = threadIdx.x - 320;              // 0..127
+    const int st = threadIdx.x - 352;              // 0..127
     const int c = st % COUT, part = st / COUT;
     const int half = (part * kPxPerPart) / 64, chunk0 = ((part * kPxPerPart) % 64) / 8;
     float acc_s[NMLP], acc_q[NMLP];
@@ -585,6 +578,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     for (int mm = 0; mm < NMLP; ++mm) flush(mm);
   } else {
     // ================= epilogue groups (warps 0-3 / 4-7) =================
+    // Each group owns two TMEM slots; its own MMA-issuing warp (9 + group) feeds them.
     const int eg = warp / 4;                 // 0: slots 0,2   1: slots 1,3
     const int quad = warp % 4;               // TMEM lane quadrant this warp may access
     const int pix_in_tile = quad * 32 + lane;
@@ -649,7 +643,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             TIMING_MARK(2);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&h_ready[s]);
+            if (lane == 0) mbar_arrive(&h_ready[s]);   // next A operand complete (4 warps arrive)
           } else {
             const int n = graph_n(args.n_per_graph, g, geo.N);
             // pixel coordinates with 32-bit arithmetic: one division per tile, then at most two row wraps
@@ -683,8 +677,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
                 *reinterpret_cast<uint16_t*>(my_half + c * 128 + ((my_chunk ^ (c & 7)) << 4)) = Elem<T>::bits(x);
               }
             }
-            // accumulator drained: the MMA warp may reuse the slot while the tile is being stored
-            tc_fence_before();
+            tc_fence_before();                 // accumulator drained: the slot may take its next tile
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_ready[s]);
             fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -1129,7 +1122,7 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   int grid = (int)std::min<long>((long)num_sms(), total_tiles);
   if (grid < 1) grid = 1;
   prof::begin(prof::kMlp, st);
-  tc_mlp_kernel<T, COUT, NMLP><<<grid, 448, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+  tc_mlp_kernel<T, COUT, NMLP><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
   prof::end(prof::kMlp, st);
   FGNN_LAUNCHED();
   return FGNN_OK;
