@@ -621,23 +621,27 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           tc_fence_after();
           if (!last) {
             const float* bias = (l == 0) ? (args.bias1 + ((long)g * NMLP + m) * COUT) : args.bias[m][l];
+            {
+              // all accumulator columns in flight at once: one TMEM round trip per item instead of one per 32 columns
+              uint32_t r[COUT];
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
-              uint32_t r[32];
-              tmem_ld32(lane_addr + (uint32_t)c0, r);
+              for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld32(lane_addr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
               tmem_wait_ld();
-              uint32_t h[16];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * u));
-                float x0 = __uint_as_float(r[4 * u]), x1 = __uint_as_float(r[4 * u + 1]);
-                float x2 = __uint_as_float(r[4 * u + 2]), x3 = __uint_as_float(r[4 * u + 3]);
-                add2(x0, x1, b4.x, b4.y);
-                add2(x2, x3, b4.z, b4.w);
-                h[2 * u] = Elem<T>::pack_relu(x0, x1);
-                h[2 * u + 1] = Elem<T>::pack_relu(x2, x3);
+              for (int c0 = 0; c0 < COUT; c0 += 32) {
+                uint32_t h[16];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * u));
+                  float x0 = __uint_as_float(r[c0 + 4 * u]), x1 = __uint_as_float(r[c0 + 4 * u + 1]);
+                  float x2 = __uint_as_float(r[c0 + 4 * u + 2]), x3 = __uint_as_float(r[c0 + 4 * u + 3]);
+                  add2(x0, x1, b4.x, b4.y);
+                  add2(x2, x3, b4.z, b4.w);
+                  h[2 * u] = Elem<T>::pack_relu(x0, x1);
+                  h[2 * u + 1] = Elem<T>::pack_relu(x2, x3);
+                }
+                tmem_st16(lane_addr + (uint32_t)COUT + (uint32_t)(c0 / 2), h);
               }
-              tmem_st16(lane_addr + (uint32_t)COUT + (uint32_t)(c0 / 2), h);
             }
             tmem_wait_st();
             TIMING_MARK(2);
@@ -665,15 +669,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             uint8_t* tile = s_out + (size_t)buf * (COUT * 256);
             uint8_t* my_half = tile + my_off;
             mbar_wait(&tile_empty[buf], ((uint32_t)(n_final >> 1) & 1u) ^ 1u);
+            {
+              uint32_t r[COUT];
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
-              uint32_t r[32];
-              tmem_ld32(lane_addr + (uint32_t)c0, r);
+              for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld32(lane_addr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
               tmem_wait_ld();
 #pragma unroll
-              for (int u = 0; u < 32; ++u) {
-                const int c = c0 + u;
-                const float x = (valid ? __uint_as_float(r[u]) : 0.f) + marker;
+              for (int c = 0; c < COUT; ++c) {
+                const float x = (valid ? __uint_as_float(r[c]) : 0.f) + marker;
                 *reinterpret_cast<uint16_t*>(my_half + c * 128 + ((my_chunk ^ (c & 7)) << 4)) = Elem<T>::bits(x);
               }
             }
