@@ -323,8 +323,19 @@ def main():
     if args.precision != "fp32" and kinds[dom][0] > 0:
         achieved = kind_flops[dom] / (kinds[dom][0] / 1e3) / 1e12
         peak = peaks["sustained"]
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per graph per
+        # launch, averaged over the kernel's instantiations), scaled to this run's graphs per launch
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and cfg["n"] == 500 and cfg["c"] == 64:
+            with open(tpath) as f:
+                tj = json.load(f)
+            if dom in tj:
+                graphs_per_launch = graphs_per_step * args.steps * tj[dom]["launches_per_graph_block"] * cfg["blocks"] \
+                    / max(kinds[dom][1], 1)
+                traffic = tj[dom]["dram_bytes_per_graph_launch"] * graphs_per_launch
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']}); kernel timed inside a long step",
                     "flops_per_launch": kind_flops[dom] / max(kinds[dom][1], 1),
                     "avg_launch_ms": kinds[dom][0] / max(kinds[dom][1], 1)}
