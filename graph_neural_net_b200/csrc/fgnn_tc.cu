@@ -287,7 +287,7 @@ constexpr int kSlots = 4;
 
 // Optional cycle accounting of the conv-chain kernel's roles (compile with -DFGNN_TC_TIMING; bring-up only).
 #ifdef FGNN_TC_TIMING
-__device__ unsigned long long g_tc_timing[16];
+__device__ unsigned long long g_tc_timing[24];
 #define TIMING_DECL long long tm_t0 = clock64(), tm_acc[6] = {0, 0, 0, 0, 0, 0}
 #define TIMING_MARK(slot) do { long long tm_t1 = clock64(); tm_acc[slot] += tm_t1 - tm_t0; tm_t0 = tm_t1; } while (0)
 #define TIMING_FLUSH(base, cond) do { if (cond) for (int tm_i = 0; tm_i < 6; ++tm_i) atomicAdd(&g_tc_timing[(base) + tm_i], (unsigned long long)tm_acc[tm_i]); } while (0)
@@ -354,7 +354,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 2); }
     mbar_init(wh_full, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&h_ready[s], 4); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_empty[s], 5); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&tile_full[s], 4); mbar_init(&tile_empty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
@@ -365,18 +365,20 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
 
   // graph walker shared by all roles: flat tile t -> (graph g, first pixel p0); t must not decrease
   struct Walker {
-    int g = 0;
+    int g = 0, n = 0;
     long base = 0, tiles = 0;
   };
   auto walker_init = [&](Walker& w) {
     w.g = 0;
     w.base = 0;
+    w.n = graph_n(args.n_per_graph, 0, geo.N);
     w.tiles = mlp_tiles(args.n_per_graph, 0, geo);
   };
   auto walker_seek = [&](Walker& w, long t) {
     while (t >= w.base + w.tiles) {
       w.base += w.tiles;
       ++w.g;
+      w.n = graph_n(args.n_per_graph, w.g, geo.N);
       w.tiles = mlp_tiles(args.n_per_graph, w.g, geo);
     }
   };
@@ -491,6 +493,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       for (int s = eg; s < kSlots; s += 2)     // prime both slots with the first wave
         if (s < V) issue_layer1(s, s);
       uint32_t ph_h = 0;                       // phase bits of h_ready[s]
+      TIMING_DECL;
       for (long v0 = 0; v0 < V; v0 += kSlots) {
 #pragma unroll 1
         for (int l = 0; l < depth; ++l) {
@@ -499,13 +502,16 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             const long v = v0 + s;
             if (v >= V) break;
             const int m = (int)(v % NMLP);
+            TIMING_MARK(0);
             mbar_wait(&h_ready[s], (ph_h >> s) & 1u);   // epilogue of (v, l) done: operand written / accumulator drained
             ph_h ^= 1u << s;
-            if (l < depth - 1) issue_hidden(s, m, l + 1);
-            else if (v + kSlots < V) issue_layer1(v + kSlots, s);
+            TIMING_MARK(2);
+            if (l < depth - 1) { issue_hidden(s, m, l + 1); TIMING_MARK(4); }
+            else if (v + kSlots < V) { issue_layer1(v + kSlots, s); TIMING_MARK(3); }
           }
         }
       }
+      TIMING_FLUSH(0, warp == 9 && lane == 0);
       Walker wl = wi;                          // the producer may still wait for this group's release of later graphs
       walker_seek(wl, t_end - 1);
       release_graphs_upto(wl.g - g_first + 1);
@@ -533,7 +539,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     Walker w;
     walker_init(w);
     int items[2] = {0, 0};                         // final items consumed per epilogue group
+    TIMING_DECL;
     for (long v = 0; v < V; ++v) {
+      TIMING_MARK(0);
       const int b = (int)(v & 1);                  // epilogue group (= slot parity) that produced this tile
       const int kb = (b == 0) ? items[0]++ : items[1]++;
       const int buf = b * 2 + (kb & 1);
@@ -544,7 +552,23 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
 #pragma unroll
       for (int mm = 0; mm < NMLP; ++mm)
         if (mm == m && g != acc_g[mm]) { flush(mm); acc_g[mm] = g; }
+      TIMING_MARK(1);
       mbar_wait(&tile_full[buf], (uint32_t)(kb >> 1) & 1u);
+      TIMING_MARK(2);
+      if (st == 0) {
+        // the four epilogue warps have staged the tile and fenced it for the async proxy: store it (one 64-pixel
+        // half per TMA; a half never straddles a row because NPC % 64 == 0)
+        const CUtensorMap* mo = (m == 0) ? &map_o0 : &map_o1;
+        const int mode = args.out_mode[m];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int ph = p0 + hf * 64;
+          const int prw = ph / geo.NPC, col = ph - prw * geo.NPC;
+          const int prow = (mode == kOutA) ? prw + prw / kTM1 : (mode == kOutB ? prw + prw / geo.TN1 : prw);
+          if (prw < geo.N) tma_store_3d(mo, s_out + (size_t)buf * (COUT * 256) + (size_t)hf * (COUT * 128), col, prow, g * COUT);
+        }
+        bulk_commit_group();
+      }
       const uint8_t* row = s_out + (size_t)buf * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
       float sv = 0.f, qv = 0.f;
 #pragma unroll
@@ -571,9 +595,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
 #pragma unroll
       for (int mm = 0; mm < NMLP; ++mm)
         if (mm == m) { acc_s[mm] += sv; acc_q[mm] += qv; }
+      TIMING_MARK(3);
+      if (st == 0) bulk_wait_group_read0();      // the store has read the staged tile (it ran under the statistics pass)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tile_empty[buf]);
+      TIMING_MARK(4);
     }
+    TIMING_FLUSH(16, st == 0);
+    if (st == 0) bulk_wait_group0();             // every store has landed before the CTA exits
 #pragma unroll
     for (int mm = 0; mm < NMLP; ++mm) flush(mm);
   } else {
@@ -582,16 +611,13 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     const int eg = warp / 4;                 // 0: slots 0,2   1: slots 1,3
     const int quad = warp % 4;               // TMEM lane quadrant this warp may access
     const int pix_in_tile = quad * 32 + lane;
-    const int et = threadIdx.x - eg * 128;   // thread index inside the group
     uint32_t ph_mma = 0;                     // phase bits of mma_done[s]
     int n_final = 0;                         // final-layer items this group has produced (staging buffer = n_final & 1)
     Walker w;
     walker_init(w);
-    int slot_g0 = 0, slot_g1 = 0;            // (graph, first tile of graph) of the tile in this group's two slots
+    int slot_g0 = 0, slot_g1 = 0, slot_n0 = 0, slot_n1 = 0;   // (graph, its n, first tile of graph) of the tile in this group's two slots
     long slot_base0 = 0, slot_base1 = 0;
     // staged output tiles of this group: 2 buffers x [half][COUT rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
-    const size_t my_off = (size_t)(pix_in_tile >> 6) * (COUT * 128) + (pix_in_tile & 7) * 2;
-    const int my_chunk = (pix_in_tile & 63) >> 3;
 
     TIMING_DECL;
     for (long v0 = 0; v0 < V; v0 += kSlots) {
@@ -611,7 +637,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           const bool second = s >= 2;
           if (l == 0) {
             walker_seek(w, t_begin + seq);
-            if (second) { slot_g1 = w.g; slot_base1 = w.base; } else { slot_g0 = w.g; slot_base0 = w.base; }
+            if (second) { slot_g1 = w.g; slot_n1 = w.n; slot_base1 = w.base; } else { slot_g0 = w.g; slot_n0 = w.n; slot_base0 = w.base; }
           }
           const int g = second ? slot_g1 : slot_g0;
           const long gbase = second ? slot_base1 : slot_base0;
@@ -649,7 +675,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_ready[s]);   // next A operand complete (4 warps arrive)
           } else {
-            const int n = graph_n(args.n_per_graph, g, geo.N);
+            const int n = second ? slot_n1 : slot_n0;
             // pixel coordinates with 32-bit arithmetic: one division per tile, then at most two row wraps
             const int p0 = (int)(t_begin + seq - gbase) * kTileM;
             int pi = p0 / geo.NPC;
@@ -667,39 +693,52 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             // has read it too (thread 0 of the group arrives for the store, see below)
             const int buf = eg * 2 + (n_final & 1);
             uint8_t* tile = s_out + (size_t)buf * (COUT * 256);
-            uint8_t* my_half = tile + my_off;
             mbar_wait(&tile_empty[buf], ((uint32_t)(n_final >> 1) & 1u) ^ 1u);
+            TIMING_MARK(3);
             {
-              uint32_t r[COUT];
+              // Transposing store: the 16x256b TMEM load hands every thread channel PAIRS of four pixels (the mma
+              // C-fragment layout), one packed convert per pair, and stmatrix.trans writes 8 channels x 8 pixels as
+              // eight 16-byte row pieces -> 8 stmatrix per warp instead of 64 two-byte stores per thread.
+              const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+              const uint32_t mmask = __ballot_sync(0xffffffffu, marker != 0.f);
+              uint32_t rl[COUT / 2], ru[COUT / 2];
+              if constexpr (COUT == 64) {
+                tmem_ld_16x256b_x8(lane_addr, rl);
+                tmem_ld_16x256b_x8(lane_addr + (16u << 16), ru);
+              } else {
+                tmem_ld_16x256b_x4(lane_addr, rl);
+                tmem_ld_16x256b_x4(lane_addr + (16u << 16), ru);
+              }
+              const int q4 = lane >> 2;
+              const uint32_t one2 = Elem<T>::pack(1.f, 1.f);
+              bool vb[4];
+              uint32_t fill[4];
 #pragma unroll
-              for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld32(lane_addr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
+              for (int i = 0; i < 4; ++i) {
+                vb[i] = (vmask >> (8 * i + q4)) & 1u;
+                fill[i] = ((mmask >> (8 * i + q4)) & 1u) ? one2 : 0u;
+              }
+              // this thread supplies the address of row (lane % 8) of matrix (lane / 8): channel 8u + lane % 8,
+              // pixels quad * 32 + 8 * (lane / 8) .. + 7 = 16-byte chunk (quad & 1) * 4 + lane / 8 of half quad / 2
+              const uint32_t st_addr = smem_u32(tile) + (uint32_t)(quad >> 1) * (COUT * 128) + (uint32_t)(lane & 7) * 128 +
+                                       (uint32_t)(((((quad & 1) << 2) + (lane >> 3)) ^ (lane & 7)) << 4);
               tmem_wait_ld();
 #pragma unroll
-              for (int c = 0; c < COUT; ++c) {
-                const float x = (valid ? __uint_as_float(r[c]) : 0.f) + marker;
-                *reinterpret_cast<uint16_t*>(my_half + c * 128 + ((my_chunk ^ (c & 7)) << 4)) = Elem<T>::bits(x);
+              for (int u = 0; u < COUT / 8; ++u) {
+                const uint32_t w0 = vb[0] ? Elem<T>::pack(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
+                const uint32_t w1 = vb[1] ? Elem<T>::pack(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
+                const uint32_t w2 = vb[2] ? Elem<T>::pack(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
+                const uint32_t w3 = vb[3] ? Elem<T>::pack(__uint_as_float(ru[4 * u + 2]), __uint_as_float(ru[4 * u + 3])) : fill[3];
+                stmatrix_x4_trans(st_addr + (uint32_t)u * 1024u, w0, w1, w2, w3);
               }
             }
+            TIMING_MARK(4);
             tc_fence_before();                 // accumulator drained: the slot may take its next tile
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_ready[s]);
             fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
-            named_bar_sync(1 + eg, 128);
-            if (et == 0) {
-              const CUtensorMap* mo = (m == 0) ? &map_o0 : &map_o1;
-#pragma unroll
-              for (int hf = 0; hf < 2; ++hf) {
-                const int ph = p0 + hf * 64;                 // a 64-pixel half never straddles a row (NPC % 64 == 0)
-                const int row = ph / geo.NPC, col = ph - row * geo.NPC;
-                const int prow = (mode == kOutA) ? row + row / kTM1 : (mode == kOutB ? row + row / geo.TN1 : row);
-                if (row < geo.N) tma_store_3d(mo, tile + (size_t)hf * (COUT * 128), col, prow, g * COUT);
-              }
-              bulk_commit_group();
-              mbar_arrive(&tile_full[buf]);
-              // the store issued one final item ago has finished reading the OTHER buffer -> hand it back
-              bulk_wait_group_read1();
-              if (n_final >= 1) mbar_arrive(&tile_empty[buf ^ 1]);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tile_full[buf]);   // 4 warps; the statistics warps store the tile and reduce it
             ++n_final;
             // ones rows of Y1 (layout A): the last logical row of every 127-row matmul tile writes the row below it
             if (mode == kOutA && args.ones[m] && in_plane && pi < n) {
@@ -710,13 +749,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
                 for (int c = 0; c < COUT; ++c) o1[(long)c * geo.PSA] = ov;
               }
             }
-            TIMING_MARK(3);
+            TIMING_MARK(5);
           }
-          TIMING_MARK(5);
         }
       }
     }
-    if (et == 0) bulk_wait_group0();           // all TMA stores of this group have landed before the CTA exits
     TIMING_FLUSH(8, warp == 2 && lane == 0);
   }
   tc_fence_before();
@@ -1497,18 +1534,22 @@ int debug_mlp(int precision, const fgnn_mlp_params& mp, const float* x, float* y
 
 #ifdef FGNN_TC_TIMING
 void dump_timing() {
-  unsigned long long h[16];
+  unsigned long long h[24];
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
-  const char* mma[6] = {"loop/index", "wait in_full/w1", "wait h_ready", "L1 issue+commit / fence", "hidden: 4 MMA issue", "hidden: commit"};
-  const char* epi[6] = {"loop/index", "wait mma_done", "hidden epilogue", "final epilogue", "stats flush", "fence+arrive"};
-  unsigned long long tm = 0, te = 0;
-  for (int i = 0; i < 6; ++i) { tm += h[i]; te += h[8 + i]; }
-  printf("MMA issuer (sum over CTAs, cycles):\n");
-  for (int i = 0; i < 6; ++i) printf("  %-24s %14llu %5.1f%%\n", mma[i], h[i], 100.0 * h[i] / (tm ? tm : 1));
-  printf("epilogue warp 2 (sum over CTAs, cycles):\n");
-  for (int i = 0; i < 6; ++i) printf("  %-18s %14llu %5.1f%%\n", epi[i], h[8 + i], 100.0 * h[8 + i] / (te ? te : 1));
-  unsigned long long z[16] = {0};
+  const char* names[3][6] = {
+      {"loop/index", "-", "wait h_ready", "layer-1 issue (incl. input wait)", "hidden issue+commit", "-"},
+      {"loop/index", "wait mma_done", "hidden epilogue", "final: index + wait tile_empty", "final: tmem ld + cvt + stmatrix",
+       "final: fences + arrive"},
+      {"loop", "index + stat flush", "wait tile_full", "TMA store issue + reduce", "wait store read + arrive", "-"}};
+  const char* role[3] = {"MMA issuer (warp 9)", "epilogue warp 2", "statistics thread 352"};
+  for (int r = 0; r < 3; ++r) {
+    unsigned long long tot = 0;
+    for (int i = 0; i < 6; ++i) tot += h[8 * r + i];
+    printf("%s (sum over CTAs, cycles):\n", role[r]);
+    for (int i = 0; i < 6; ++i) printf("  %-34s %14llu %5.1f%%\n", names[r][i], h[8 * r + i], 100.0 * h[8 * r + i] / (tot ? tot : 1));
+  }
+  unsigned long long z[24] = {0};
   cudaMemcpyToSymbol(g_tc_timing, z, sizeof(z));
 }
 #else
