@@ -226,6 +226,18 @@ __device__ __forceinline__ void mma_commit_e(uint64_t* bar) {
       : "memory");
 }
 
+// ---- single-thread region: `if (elect_one_sync()) { ... }` executed by the WHOLE warp under warp-uniform control
+// flow.  ptxas recognises the ELECT-derived predicate, so inside the region tcgen05.mma / commit / TMA operands move
+// to uniform registers with a plain R2UR (no waterfall loop as for `if (lane == 0)`), and a run of MMAs pays for one
+// election instead of one WARPSYNC.COLLECTIVE / ELECT / VOTEU sequence per instruction.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- tcgen05: TMEM <-> registers (32 lanes x 32-bit, N consecutive columns per thread) ---------
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

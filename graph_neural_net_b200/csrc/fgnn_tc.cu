@@ -468,26 +468,32 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
       uint32_t a_lo = a_desc_lo0 + (uint32_t)st * (stage_bytes >> 4);
       uint32_t b_lo = w1_desc_lo0 + (((uint32_t)wbuf * w1_buf_bytes + (uint32_t)m * w1_mlp_bytes) >> 4);
-      const int ksteps = K1 / 16;
+      if (elect_one_sync()) {
+        const int ksteps = K1 / 16;
 #pragma unroll 1
-      for (int k = 0; k < ksteps; ++k) {
-        mma_ss2_e(d_tmem, a_lo, a_desc_hi, b_lo, b_desc_hi, idesc1, k > 0 ? 1u : 0u);
-        a_lo += 2048u >> 4;                                       // next 16 K-rows of the MN-major tile
-        b_lo += ((k & 3) == 3) ? ((COUT * 128u - 96u) >> 4) : (32u >> 4);  // next K atom / next 32 B
+        for (int k = 0; k < ksteps; ++k) {
+          mma_ss2(d_tmem, a_lo, a_desc_hi, b_lo, b_desc_hi, idesc1, k > 0 ? 1u : 0u);
+          a_lo += 2048u >> 4;                                       // next 16 K-rows of the MN-major tile
+          b_lo += ((k & 3) == 3) ? ((COUT * 128u - 96u) >> 4) : (32u >> 4);  // next K atom / next 32 B
+        }
+        mma_commit(&in_empty[st]);             // NMLP arrivals free the input stage
+        mma_commit(&mma_done[s]);
       }
-      mma_commit_e(&in_empty[st]);             // NMLP arrivals free the input stage
-      mma_commit_e(&mma_done[s]);
+      __syncwarp();
     };
     auto issue_hidden = [&](int s, int m, int l) {   // layer l >= 1 of the tile in slot s: A = packed activations in TMEM
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
       const uint32_t wl_lo = wh_desc_lo0 + (uint32_t)(m * (depth - 1) + (l - 1)) * (wh_mat_bytes >> 4);
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int k = 0; k < COUT / 16; ++k)
-        mma_ts2_e(d_tmem, d_tmem + COUT + (uint32_t)k * 8u,
+        for (int k = 0; k < COUT / 16; ++k)
+          mma_ts2(d_tmem, d_tmem + COUT + (uint32_t)k * 8u,
                   wl_lo + (((uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u) >> 4), b_desc_hi, idesc2,
                   k > 0 ? 1u : 0u);
-      mma_commit_e(&mma_done[s]);
+        mma_commit(&mma_done[s]);
+      }
+      __syncwarp();
     };
       if (depth > 1) mbar_wait(wh_full, 0);
       for (int s = eg; s < kSlots; s += 2)     // prime both slots with the first wave
