@@ -45,6 +45,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU box.  The slow path is
 // kept out of line so that every wait site costs a handful of instructions.
+#ifdef FGNN_DEBUG_WAIT
+// Bring-up aid: a wait that exceeds ~10 ms is RECORDED (block, thread, barrier address, parity) and abandoned, so
+// that the kernel runs to completion and the host can print who was stuck on what (fgnn_debug_dump_timing()).
+__device__ unsigned int g_wait_dbg[4 + 128 * 4];
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 20000000LL) {
+      if (threadIdx.x % 32 != 0) return;
+      const unsigned int i = atomicAdd(&g_wait_dbg[0], 1u);
+      if (i < 128) {
+        g_wait_dbg[4 + 4 * i] = blockIdx.x;
+        g_wait_dbg[5 + 4 * i] = threadIdx.x;
+        g_wait_dbg[6 + 4 * i] = bar_addr;
+        g_wait_dbg[7 + 4 * i] = parity;
+      }
+      return;
+    }
+  }
+}
+#else
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t ok = 0;
@@ -64,6 +93,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) 
     }
   }
 }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
 }

@@ -299,11 +299,16 @@ __device__ unsigned long long g_tc_timing[24];
 constexpr int kMaxInStages = 4;
 __host__ __device__ inline int mlp_in_stages(int K1) { return K1 >= 128 ? 3 : 4; }   // 32 KB stages at K1 = 128
 
+// biases staged in shared memory: one folded first-layer bias vector per TMEM slot + the hidden layers' biases
+__host__ __device__ inline size_t mlp_bias_floats(int COUT, int NMLP, int depth) {
+  return (size_t)kSlots * COUT + (size_t)NMLP * (depth > 2 ? depth - 2 : 0) * COUT;
+}
+
 template <int COUT, int NMLP>
 struct MlpSmem {
   static size_t bytes(int K1, int K1g, int depth, int Kh) {
     return 1024 + (size_t)mlp_in_stages(K1) * K1 * 256 + (size_t)2 * NMLP * K1g * COUT * 2 +
-           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)4 * COUT * 256 + 512;
+           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)4 * COUT * 256 + mlp_bias_floats(COUT, NMLP, depth) * 4 + 512;
   }
 };
 
@@ -328,7 +333,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   uint8_t* s_w1 = s_in + (size_t)kInStages * stage_bytes;      // [2 buffers][NMLP][atoms][COUT][128B]
   uint8_t* s_wh = s_w1 + (size_t)2 * w1_buf_bytes;             // [NMLP][depth-1][atoms][COUT][128B]
   uint8_t* s_out = s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes;   // [2 groups][2 buffers][2 halves][COUT][128 B] swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + (size_t)4 * COUT * 256);
+  // Biases live in shared memory: with > 200 KB of it carved out the L1 holds next to nothing, and 16 global
+  // loads per epilogue pass (uniform address, L2 latency) were costing more than the rest of the pass together.
+  float* s_bias1 = reinterpret_cast<float*>(s_out + (size_t)4 * COUT * 256);   // [kSlots][COUT] folded first-layer bias of the slot's graph
+  float* s_biash = s_bias1 + kSlots * COUT;                                    // [NMLP][depth-2][COUT] biases of layers 1 .. depth-2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + (size_t)4 * COUT * 256 + mlp_bias_floats(COUT, NMLP, depth) * 4);
   uint64_t* in_full = bars;                      // [kInStages]
   uint64_t* in_empty = in_full + kMaxInStages;   // [kInStages]
   uint64_t* w1_full = in_empty + kMaxInStages;   // [2]
@@ -350,12 +359,16 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   const long V = (t_end - t_begin) * NMLP;  // virtual tiles of this CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kInStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], NMLP); }
+    for (int s = 0; s < kInStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 2); }   // both MMA warps release every stage
     for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 2); }
     mbar_init(wh_full, 1);
     for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&h_ready[s], 4); }
     for (int s = 0; s < 4; ++s) { mbar_init(&tile_full[s], 4); mbar_init(&tile_empty[s], 4); }
     fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < NMLP * (depth - 2) * COUT; i += blockDim.x) {
+    const int c = i % COUT, ml = i / COUT;
+    s_biash[i] = args.bias[ml / (depth - 2)][1 + ml % (depth - 2)][c];
   }
   if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
@@ -463,6 +476,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       if (gidx > issue_gidx) release_graphs_upto(gidx);
       const int wbuf = gidx & 1;
       mbar_wait(&w1_full[wbuf], (uint32_t)(gidx >> 1) & 1u);
+      if constexpr (NMLP == 1) {
+        // With one MLP the two issuers consume ALTERNATE tiles of the input ring.  A waiter that skips phases of an
+        // mbarrier cannot tell phase k from phase k+2 (one parity bit), so this warp also observes the other
+        // group's tile seq-1 and releases its stage; in_empty therefore always counts two arrivals and a stage
+        // cannot be refilled before both issuers have seen its current contents' phase.
+        if (seq > 0) {
+          const long q = seq - 1;
+          const int sq = (int)(q % kInStages);
+          mbar_wait(&in_full[sq], (uint32_t)(q / kInStages) & 1u);
+          if (lane == 0) mbar_arrive(&in_empty[sq]);
+          __syncwarp();
+        }
+      }
       mbar_wait(&in_full[st], (uint32_t)(seq / kInStages) & 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
@@ -621,6 +647,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     int n_final = 0;                         // final-layer items this group has produced (staging buffer = n_final & 1)
     Walker w;
     walker_init(w);
+    const int et = threadIdx.x - eg * 128;   // thread index inside the group
+    int bias_g0 = -1, bias_g1 = -1;          // graph whose folded first-layer bias sits in s_bias1[slot]
     int slot_g0 = 0, slot_g1 = 0, slot_n0 = 0, slot_n1 = 0;   // (graph, its n, first tile of graph) of the tile in this group's two slots
     long slot_base0 = 0, slot_base1 = 0;
     // staged output tiles of this group: 2 buffers x [half][COUT rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
@@ -647,12 +675,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           }
           const int g = second ? slot_g1 : slot_g0;
           const long gbase = second ? slot_base1 : slot_base0;
+          if (l == 0 && depth > 1 && g != (second ? bias_g1 : bias_g0)) {
+            // first tile of a new graph in this slot (m is fixed per slot: NMLP divides kSlots).  All four warps of the
+            // group take this branch at the same item, and the previous tile's layer-0 pass is long finished.
+            if (et < COUT) s_bias1[s * COUT + et] = __ldg(args.bias1 + ((long)g * NMLP + m) * COUT + et);
+            named_bar_sync(1 + eg, 128);
+            if (second) bias_g1 = g; else bias_g0 = g;
+          }
           mbar_wait(&mma_done[s], (ph_mma >> s) & 1u);
           ph_mma ^= 1u << s;
           TIMING_MARK(1);
           tc_fence_after();
           if (!last) {
-            const float* bias = (l == 0) ? (args.bias1 + ((long)g * NMLP + m) * COUT) : args.bias[m][l];
+            const float* bias = (l == 0) ? (s_bias1 + s * COUT) : (s_biash + (m * (depth - 2) + (l - 1)) * COUT);
             {
               // all accumulator columns in flight at once: one TMEM round trip per item instead of one per 32 columns
               uint32_t r[COUT];
@@ -664,7 +699,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
                 uint32_t h[16];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * u));
+                  const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + 4 * u);
                   float x0 = __uint_as_float(r[c0 + 4 * u]), x1 = __uint_as_float(r[c0 + 4 * u + 1]);
                   float x2 = __uint_as_float(r[c0 + 4 * u + 2]), x3 = __uint_as_float(r[c0 + 4 * u + 3]);
                   add2(x0, x1, b4.x, b4.y);
@@ -1559,7 +1594,20 @@ void dump_timing() {
   cudaMemcpyToSymbol(g_tc_timing, z, sizeof(z));
 }
 #else
-void dump_timing() {}
+void dump_timing() {
+#ifdef FGNN_DEBUG_WAIT
+  unsigned int h[4 + 128 * 4];
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("sync: %s\n", cudaGetErrorString(e));
+  cudaMemcpyFromSymbol(h, ptx::g_wait_dbg, sizeof(h));
+  printf("abandoned waits: %u\n", h[0]);
+  for (unsigned i = 0; i < h[0] && i < 128; ++i)
+    printf("  block %3u thread %3u (warp %2u lane %2u) barrier smem+0x%x parity %u\n", h[4 + 4 * i], h[5 + 4 * i], h[5 + 4 * i] / 32,
+           h[5 + 4 * i] % 32, h[6 + 4 * i], h[7 + 4 * i]);
+  unsigned int z[4] = {0, 0, 0, 0};
+  cudaMemcpyToSymbol(ptx::g_wait_dbg, z, sizeof(z));
+#endif
+}
 #endif
 
 }  // namespace tc
