@@ -75,18 +75,26 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) 
 }
 #else
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
+  // The loop is three instructions: a quarter of all issue slots of the conv-chain kernel used to go to polling
+  // (try_wait + clock read + compare per spin, ~10 waiting warps per SM, and the waiting control warps have the
+  // highest scheduling priority).  try_wait suspends the warp in hardware for a short, implementation-defined
+  // time (a suspend-time hint turns it into NANOSLEEP.SYNCS, whose wake-up latency cost 3% end to end); the 2 s
+  // watchdog is only evaluated every 1024 spins.
   const long long t0 = clock64();
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
-        : "memory");
-    // (no software back-off: try_wait already suspends the warp in hardware and wake-up latency is on the critical path)
-    if (!ok && clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+  for (;;) {
+#pragma unroll 1
+    for (int spins = 0; spins < 1024; ++spins) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity)
+          : "memory");
+      if (ok) return;
+    }
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       printf("fgnn: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              bar_addr, parity);
       __trap();
@@ -94,6 +102,8 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) 
   }
 }
 #endif
+// (A suspend-time hint on try_wait -- NANOSLEEP.SYNCS instead of polling -- was measured 3-5% slower end to end,
+// for the control roles as well: every hand-off in the conv-chain kernel is latency-critical.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
 }
@@ -305,6 +315,20 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 128 bit per step (4 columns): thread t stores r[2k] to lane t/4 and r[2k+1] to lane t/4 + 8, column
+// 4k + t%4 -- the packed-pair image of the 16x256b load fragment (columns 8k + 2(t%4), +1 -> one 16-bit pair).
+__device__ __forceinline__ void tmem_st_16x128b_x8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 // four transposed 8x8 b16 matrices: matrix i takes register r_i; thread t holds elements (col t/4, rows 2(t%4), +1)
 // in the (low, high) halves of r_i; row r of matrix i (16 bytes) goes to the address supplied by thread 8i + r
 __device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
@@ -361,6 +385,13 @@ __device__ __forceinline__ void add2(float& a, float& b, float c, float d) {
       "add.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
       : "+f"(a), "+f"(b)
       : "f"(c), "f"(d));
+}
+// (qa, qb) += (x * x, y * y) and (sa, sb) += (x, y) as packed fp32x2 operations
+__device__ __forceinline__ void sum_sq2(float& sa, float& sb, float& qa, float& qb, float x, float y) {
+  asm("{\n\t.reg .b64 v, s, q;\n\tmov.b64 v, {%4, %5};\n\tmov.b64 s, {%0, %1};\n\tmov.b64 q, {%2, %3};\n\t"
+      "add.rn.f32x2 s, s, v;\n\tfma.rn.f32x2 q, v, v, q;\n\tmov.b64 {%0, %1}, s;\n\tmov.b64 {%2, %3}, q;\n\t}"
+      : "+f"(sa), "+f"(sb), "+f"(qa), "+f"(qb)
+      : "f"(x), "f"(y));
 }
 template <> struct Elem<__nv_bfloat16> {
   static constexpr int kFmt = 1;

@@ -603,16 +603,20 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       }
       const uint8_t* row = s_out + (size_t)buf * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
       float sv = 0.f, qv = 0.f;
+      {
+        float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;    // even / odd pixels, packed fp32x2 arithmetic
 #pragma unroll
-      for (int k = 0; k < kPxPerPart / 8; ++k) {
-        const uint4 wv = *reinterpret_cast<const uint4*>(row + (((chunk0 + k) ^ (c & 7)) << 4));
-        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        for (int k = 0; k < kPxPerPart / 8; ++k) {
+          const uint4 wv = *reinterpret_cast<const uint4*>(row + (((chunk0 + k) ^ (c & 7)) << 4));
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float2 f = Elem<T>::unpack2(ww[u]);
-          sv += f.x + f.y;
-          qv = fmaf(f.x, f.x, fmaf(f.y, f.y, qv));
+          for (int u = 0; u < 4; ++u) {
+            const float2 f = Elem<T>::unpack2(ww[u]);
+            sum_sq2(sa, sb, qa, qb, f.x, f.y);
+          }
         }
+        sv = sa + sb;
+        qv = qa + qb;
       }
       // hole pixels hold a marker (0 or 1), not data: take them out again
       for (int hp = (geo.BN - 1 - (p0 & (geo.BN - 1))) & (geo.BN - 1); hp < 128; hp += geo.BN) {
