@@ -165,7 +165,10 @@ fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf) {
   __syncthreads();
   T* wg = wf + ((long)g * a.nmlp + m) * a.c_out * a.K1g;
   const float* w = a.w[m];
-  for (int idx = threadIdx.x; idx < a.c_out * a.K1g; idx += blockDim.x) {
+  // output channels are split over gridDim.z: the kernel is latency-bound, 19 us with G x nmlp CTAs
+  const int co_per = (a.c_out + gridDim.z - 1) / gridDim.z;
+  const int co_begin = blockIdx.z * co_per, co_end = min(a.c_out, co_begin + co_per);
+  for (int idx = co_begin * a.K1g + threadIdx.x; idx < co_end * a.K1g; idx += blockDim.x) {
     const int co = idx / a.K1g, k = idx % a.K1g;
     float v = 0.f;
     int col = -1;
@@ -176,7 +179,7 @@ fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf) {
   }
   // folded bias: one warp per output channel
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  for (int co = warp; co < a.c_out; co += blockDim.x / 32) {
+  for (int co = co_begin + warp; co < co_end; co += blockDim.x / 32) {
     float acc = 0.f;
     for (int col = lane; col < cin; col += 32) acc = fmaf(w[co * cin + col], s_s[col], acc);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -832,7 +835,9 @@ template <int BN>
 struct MatmulCfg {
   static constexpr int kStageBytes = 128 * 128 + BN * 128;  // A: 128 rows x 64 k, B: 64 k x BN
   static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 2 * BN * sizeof(float) + 256;
+  static constexpr int kStoreBytes = 4 * 2 * 32 * 128;      // per epilogue warp: 2 buffers of 32 rows x 64 columns
+  static constexpr size_t kSmemBytes =
+      (size_t)kStages * kStageBytes + kStoreBytes + 2 * BN * sizeof(float) + (2 * kStages + 4) * 8 + 16;   // + barriers, TMEM slot
 };
 
 struct TileWalker {
@@ -872,13 +877,18 @@ struct TileWalker {
 template <typename T, int BN>
 __global__ void __launch_bounds__(192, 1)
 tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_o31,
                  const MatmulArgs<T> args) {
   using Cfg = MatmulCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_cc = reinterpret_cast<float*>(smem + (size_t)kStages * Cfg::kStageBytes);  // [2][BN]
+  // No static shared memory in this kernel, so the dynamic window starts 1024-byte aligned (checked: the swizzled TMA /
+  // UMMA tiles need it, and at BN = 256 there is no room left for alignment slack).
+  extern __shared__ uint8_t smem_mm[];
+  uint8_t* smem = smem_mm;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* s_store = smem + (size_t)kStages * Cfg::kStageBytes;                        // [4 warps][2][32 rows][128 B]
+  float* s_cc = reinterpret_cast<float*>(s_store + Cfg::kStoreBytes);                  // [2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_cc + 2 * BN);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
@@ -976,6 +986,7 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
     int as = 0;
     uint32_t aphase = 0;
+    int sbuf = 0;                            // staging buffer of the next 64-column chunk
     for (long t = blockIdx.x; t < total; t += gridDim.x) {
       int q, m, nn, n;
       tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
@@ -1009,34 +1020,52 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const float scale = a1 * a2;
       const float rc = fmaf(a1 * s2, r1, s1 * s2 * (float)n);
       const bool row_ok = (r < kTM1) && (i < n);
-      T* orow = args.out + (long)q * geo.PSC + (long)i * geo.NPC + (long)nn * BN;
       const int jlog0 = nn * geo.TN1;        // logical column of tile column 0
+      // The tile leaves through shared memory and TMA: every warp stages 64-column chunks of its 32 rows (128-byte
+      // rows, 16-byte pieces XOR-swizzled by row) and stores them as one box.  Direct stores -- 16 bytes per thread
+      // at a row pitch of NPC * 2 bytes -- were partial-sector writes and cost 40% of this kernel.  The quadrant
+      // that ends with the ones row stores a 31-row box (row 127 belongs to the next row tile).
+      const CUtensorMap* mo = (quad == 3) ? &map_o31 : &map_o32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld32(taddr + (uint32_t)c0, rr);
-        tmem_wait_ld();
-        if (row_ok && jlog0 + c0 < n) {
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        if (jlog0 + c0 >= n) break;          // columns beyond the graph: nothing to write (warp-uniform)
+        uint8_t* buf = s_store + (size_t)(quad * 2 + sbuf) * 4096;
+        if (lane == 0) bulk_wait_group_read1();   // the store issued two chunks ago has read this buffer
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t rr[32];
+          tmem_ld32(taddr + (uint32_t)(c0 + 32 * h), rr);
+          tmem_wait_ld();
           uint32_t pk[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const int ca = c0 + 2 * u, cb = ca + 1;
+            const int ca = c0 + 32 * h + 2 * u, cb = ca + 1;
             float x0 = fmaf(scale, __uint_as_float(rr[2 * u]), rc + cc[ca]);
             float x1 = fmaf(scale, __uint_as_float(rr[2 * u + 1]), rc + cc[cb]);
-            if (ca == BN - 1 || jlog0 + ca >= n) x0 = 0.f;   // hole column / beyond the graph: keep zeros
-            if (cb == BN - 1 || jlog0 + cb >= n) x1 = 0.f;
+            if (!row_ok || ca == BN - 1 || jlog0 + ca >= n) x0 = 0.f;   // hole column / beyond the graph: zeros
+            if (!row_ok || cb == BN - 1 || jlog0 + cb >= n) x1 = 0.f;
             pk[u] = Elem<T>::pack(x0, x1);
           }
 #pragma unroll
           for (int vv = 0; vv < 4; ++vv)
-            *reinterpret_cast<uint4*>(orow + c0 + vv * 8) = make_uint4(pk[4 * vv], pk[4 * vv + 1], pk[4 * vv + 2], pk[4 * vv + 3]);
+            *reinterpret_cast<uint4*>(buf + lane * 128 + (((h * 4 + vv) ^ (lane & 7)) << 4)) =
+                make_uint4(pk[4 * vv], pk[4 * vv + 1], pk[4 * vv + 2], pk[4 * vv + 3]);
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(mo, buf, nn * BN + c0, m * kTM1 + quad * 32, q);
+          bulk_commit_group();
+        }
+        sbuf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) bulk_wait_group0();       // this warp's stores have landed before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -1114,6 +1143,10 @@ int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const f
   // K = physical column of Y1 (layout A) = physical row of Y2 (layout B); reads past either extent are zero filled
   if (int e = make_map3(&ma, is_bf16, y1, geo.NPC, geo.PRA, planes, geo.NPC, (uint64_t)geo.PSA, 64, 128)) return e;
   if (int e = make_map3(&mb, is_bf16, y2, geo.NPC, geo.PRB, planes, geo.NPC, (uint64_t)geo.PSB, 64, 64)) return e;
+  // output (layout C) as 64-column x 32-row (31 for the quadrant that ends with the ones row) store boxes
+  CUtensorMap mo32, mo31;
+  if (int e = make_map3(&mo32, is_bf16, out, geo.NPC, geo.N, planes, geo.NPC, (uint64_t)geo.PSC, 64, 32)) return e;
+  if (int e = make_map3(&mo31, is_bf16, out, geo.NPC, geo.N, planes, geo.NPC, (uint64_t)geo.PSC, 64, 31)) return e;
   MatmulArgs<T> a{G, C, geo, out, coef_a, coef_b, npg};
   const int grid = num_sms();
 #define FGNN_MM_LAUNCH(BNV)                                                                              \
@@ -1124,7 +1157,7 @@ int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const f
                                      (int)MatmulCfg<BNV>::kSmemBytes));                                  \
       attr = true;                                                                                       \
     }                                                                                                    \
-    tc_matmul_kernel<T, BNV><<<grid, 192, MatmulCfg<BNV>::kSmemBytes, st>>>(ma, mb, a);                   \
+    tc_matmul_kernel<T, BNV><<<grid, 192, MatmulCfg<BNV>::kSmemBytes, st>>>(ma, mb, mo32, mo31, a);                   \
   } while (0)
   prof::begin(prof::kMatmul, st);
   if (geo.BN == 64) FGNN_MM_LAUNCH(64);
@@ -1256,7 +1289,7 @@ int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int3
   fa.c_out = C;
   fa.K1g = round_up(round_up(M.c_src[0], 16) + (M.nsrc > 1 ? round_up(M.c_src[1], 16) : 0), 64);
   FGNN_CHECK_ARG(fa.c[0] + fa.c[1] <= 512, "too many input channels for the fold kernel");
-  fold_weights_kernel<T><<<dim3(G, M.nmlp), 256, 0, st>>>(fa, M.wf, M.bf);
+  fold_weights_kernel<T><<<dim3(G, M.nmlp, 8), 256, 0, st>>>(fa, M.wf, M.bf);
   FGNN_LAUNCHED();
   MlpLaunch<T> L{};
   L.nmlp = M.nmlp;
