@@ -181,3 +181,35 @@ def test_headline_size_properties(prec):
     assert err < (2e-2 if prec == "fp16" else 1e-1)
     assert rel_fro(solo[0].cpu(), e[1].cpu()) < (2e-2 if prec == "fp16" else 1e-1)
     assert rel_fro(ragged.tensor.rename(None)[0, :, :n].cpu(), e[1].cpu()) < (2e-2 if prec == "fp16" else 1e-1)
+
+
+def test_bench_sized_launches_are_stable():
+    """Regression for the input-ring phase aliasing: it needed BENCH-sized launches -- dozens of
+    n=500 graphs per conv-chain launch, so that every CTA runs hundreds of tiles and the consumer can catch up with
+    the TMA loads -- and showed as a GPU fault or a deadlock, never in the small parity cases.  52 graphs (two
+    chunks) are embedded several times; every run must finish, agree with the first one to rounding (statistics
+    are reduced with atomics) and graph 0 / graph 51 must agree with embedding them alone."""
+    gen = torch.Generator().manual_seed(99)
+    n, c, G = 500, 64, 52
+    sd = O.xavier_state_dict(2, c, 4, 3, gen)
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=4,
+                    in_features=c, out_features=c, depth_of_mlp=3)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    base = (torch.rand((4, n, n), generator=gen) < 0.2).float()
+    base = torch.triu(base, 1)
+    base = base + base.transpose(1, 2)
+    x = torch.stack([O.adjacency_to_features(base[i % 4][torch.randperm(n, generator=gen)][:, torch.randperm(n, generator=gen)])
+                     for i in range(G)]).to(DEV)
+    with torch.no_grad():
+        first = model.node_embedder.forward_fused(x, "bf16")
+        torch.cuda.synchronize()
+        for _ in range(4):
+            again = model.node_embedder.forward_fused(x, "bf16")
+            torch.cuda.synchronize()
+            assert torch.isfinite(again).all()
+            assert rel_fro(again.cpu(), first.cpu()) < 1e-3
+        for i in (0, G - 1):
+            solo = model.node_embedder.forward_fused(x[i:i + 1], "bf16")
+            assert rel_fro(solo[0].cpu(), first[i].cpu()) < 1e-1

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-for c in 1 2 4 8 16 37; do
+for c in 2 4 8 16 32; do
   echo "== FGNN_TC_CHUNK=$c"
   FGNN_TC_CHUNK=$c python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
