@@ -66,6 +66,15 @@ Geo make_geo(int N) {
 __device__ __forceinline__ int graph_n(const int32_t* n_per_graph, int g, int N) {
   return n_per_graph ? n_per_graph[g] : N;
 }
+// order-preserving float <-> unsigned code (0 is below every float, so a zeroed buffer is "no value yet")
+__device__ __forceinline__ unsigned int enc_ordered(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned int e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
 // one past the last physical K index (column of Y1 / row of Y2) a graph with n vertices uses
 __device__ __forceinline__ int phys_k_end(int n, int TN1) { return (n - 1) + (n - 1) / TN1 + 1; }
 // logical rows of a plane that the conv kernels must cover so that K-loops of the matmul may over-read zeros
@@ -187,6 +196,24 @@ fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf) {
   }
 }
 
+// emb[g][c][i] = max_j (a y[i][j] + s) from the row-wise max / min codes the conv chain left in rowenc (rows >= n -> 0)
+__global__ void pool_finalize_kernel(const unsigned int* __restrict__ rowenc, const float* __restrict__ coef,
+                                     float* __restrict__ emb, int C, int N, long total, const int32_t* __restrict__ n_per_graph) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int i = (int)(idx % N);
+  const long gc = idx / N;
+  const int g = (int)(gc / C);
+  const int n = graph_n(n_per_graph, g, N);
+  float out = 0.f;
+  if (i < n) {
+    const float a = coef[2 * gc], sft = coef[2 * gc + 1];
+    const float mx = dec_ordered(rowenc[2 * idx]), mn = -dec_ordered(rowenc[2 * idx + 1]);
+    out = fmaf(a, a >= 0.f ? mx : mn, sft);
+  }
+  emb[idx] = out;
+}
+
 // (sum, sum of squares) accumulated by the conv-chain epilogue -> GraphNorm scale / shift.
 //   acc[g][m][c][2] (double)  ->  coef_m[g][c] = {a, s}
 struct CoefArgs {
@@ -215,46 +242,6 @@ __global__ void finalize_coef_kernel(CoefArgs a, int total) {
   a.coef[m][((long)g * a.C + c) * 2 + 1] = (float)((double)(a.gb[m] ? a.gb[m][c] : 0.f) - sc * mean);
 }
 
-// emb[g][c][i] = max_{j<n} (a*y[i][j] + s); rows >= n -> 0   (layers.py:194-203 on folded data, layout C)
-// One warp per row, 16-byte loads (8 elements); hole columns and columns beyond n are masked by index.
-template <typename T>
-__global__ void __launch_bounds__(256)
-pool_kernel(const T* __restrict__ y, const float* __restrict__ coef, float* __restrict__ emb, int C, Geo geo,
-            long rows, const int32_t* __restrict__ n_per_graph) {
-  const long row = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-  if (row >= rows) return;
-  const int lane = threadIdx.x % 32;
-  const int i = (int)(row % geo.N);
-  const long q = row / geo.N;
-  const int g = (int)(q / C);
-  const int n = graph_n(n_per_graph, g, geo.N);
-  float out = 0.f;
-  if (i < n) {
-    const uint4* r = reinterpret_cast<const uint4*>(y + q * geo.PSC + (long)i * geo.NPC);
-    const int pj_end = (n - 1) + (n - 1) / geo.TN1 + 1;     // one past the last valid physical column
-    float mx = -INFINITY, mn = INFINITY;
-    for (int v = lane; v * 8 < pj_end; v += 32) {
-      const uint4 w = __ldg(r + v);
-      const T* e = reinterpret_cast<const T*>(&w);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int pj = v * 8 + u;
-        if (pj < pj_end && (pj & (geo.BN - 1)) != geo.BN - 1) {
-          const float x = Elem<T>::to_float(e[u]);
-          mx = fmaxf(mx, x);
-          mn = fminf(mn, x);
-        }
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    const float a = coef[2 * q], s = coef[2 * q + 1];
-    out = (a >= 0.f) ? fmaf(a, mx, s) : fmaf(a, mn, s);
-  }
-  if (lane == 0) emb[row] = out;
-}
 
 // =============================================================================================
 // K_A: fused conv chains on tensor cores, software-pipelined over kSlots tiles in flight.
@@ -283,6 +270,10 @@ struct MlpArgs {
   int out_mode[2];                           // kOutC / kOutA / kOutB
   int ones[2];                               // kOutA: write the ones rows; kOutB: holes hold ones
   double* stat_acc;                          // [G][NMLP][COUT][2]
+  // Fused column-max pooling (last block): when rowenc[m] is set, MLP m's tile is NOT stored; the statistics warps
+  // fold the row-wise max and min of its valid pixels into rowenc[m][g][c][i][2] (order-preserving unsigned codes
+  // of max(y) and max(-y), buffer zeroed by the caller) and pool_finalize_kernel applies the GraphNorm affine.
+  unsigned int* rowenc[2];
   const int32_t* n_per_graph;
 };
 
@@ -315,7 +306,7 @@ struct MlpSmem {
   }
 };
 
-template <typename T, int COUT, int NMLP>
+template <typename T, int COUT, int NMLP, bool POOL>
 __global__ void __launch_bounds__(480, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
               const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wh,
@@ -574,6 +565,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     Walker w;
     walker_init(w);
     int items[2] = {0, 0};                         // final items consumed per epilogue group
+    // fused pooling: running max / min of this thread's channel over the row it is currently in (consecutive tiles
+    // of a CTA are consecutive pixels, so a row spans several of them) -> one pair of atomics per row, not per tile
+    float pool_mx = -INFINITY, pool_mn = INFINITY;
+    int pool_row = -1, pool_g = -1, pool_m = 0;
+    auto pool_flush = [&]() {
+      if (pool_row >= 0 && pool_mx >= pool_mn) {
+        unsigned int* dst = args.rowenc[pool_m] + ((((long)pool_g * COUT + c) * geo.N + pool_row) << 1);
+        atomicMax(dst, enc_ordered(pool_mx));
+        atomicMax(dst + 1, enc_ordered(-pool_mn));
+      }
+      pool_mx = -INFINITY;
+      pool_mn = INFINITY;
+    };
     TIMING_DECL;
     for (long v = 0; v < V; ++v) {
       TIMING_MARK(0);
@@ -590,7 +594,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       TIMING_MARK(1);
       mbar_wait(&tile_full[buf], (uint32_t)(kb >> 1) & 1u);
       TIMING_MARK(2);
-      if (st == 0) {
+      constexpr bool pooled = POOL;                      // compile-time: the non-pooled kernels carry none of this
+      if (st == 0 && !pooled) {
         // the four epilogue warps have staged the tile and fenced it for the async proxy: store it (one 64-pixel
         // half per TMA; a half never straddles a row because NPC % 64 == 0)
         const CUtensorMap* mo = (m == 0) ? &map_o0 : &map_o1;
@@ -606,7 +611,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       }
       const uint8_t* row = s_out + (size_t)buf * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
       float sv = 0.f, qv = 0.f;
-      {
+      // fused pooling (see below): position of this thread's run, and whether all of it lies inside the graph
+      const int pstart = p0 + part * kPxPerPart;
+      const int pool_pi = pstart / geo.NPC, pool_pj0 = pstart - pool_pi * geo.NPC;
+      const bool pool_in = pooled && pool_pi < w.n && pool_pi < geo.N;
+      const int pool_pj_end = phys_k_end(w.n, geo.TN1);
+      const bool pool_full = pool_in && pool_pj0 + kPxPerPart <= pool_pj_end;      // warp-uniform (part is per warp)
+      if (pooled && (pool_pi != pool_row || g != pool_g || m != pool_m)) {
+        pool_flush();
+        pool_row = pool_in ? pool_pi : -1;
+        pool_g = g;
+        pool_m = m;
+      }
+      if (!pool_full) {
         float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;    // even / odd pixels, packed fp32x2 arithmetic
 #pragma unroll
         for (int k = 0; k < kPxPerPart / 8; ++k) {
@@ -620,6 +637,28 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         }
         sv = sa + sb;
         qv = qa + qb;
+      } else {
+        // same pass with the row max / min folded in.  A hole column can only be the LAST pixel of a run (runs start
+        // at multiples of kPxPerPart, BN is a multiple of 64): one guarded element, no per-pixel tests.
+        const bool last_hole = ((pool_pj0 + kPxPerPart - 1) & (geo.BN - 1)) == geo.BN - 1;
+        float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, mx = pool_mx, mn = pool_mn;
+#pragma unroll
+        for (int k = 0; k < kPxPerPart / 8; ++k) {
+          const uint4 wv = *reinterpret_cast<const uint4*>(row + (((chunk0 + k) ^ (c & 7)) << 4));
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 f = Elem<T>::unpack2(ww[u]);
+            sum_sq2(sa, sb, qa, qb, f.x, f.y);
+            mx = fmaxf(mx, f.x);
+            mn = fminf(mn, f.x);
+            if (k < kPxPerPart / 8 - 1 || u < 3 || !last_hole) { mx = fmaxf(mx, f.y); mn = fminf(mn, f.y); }
+          }
+        }
+        sv = sa + sb;
+        qv = qa + qb;
+        pool_mx = mx;
+        pool_mn = mn;
       }
       // hole pixels hold a marker (0 or 1), not data: take them out again
       for (int hp = (geo.BN - 1 - (p0 & (geo.BN - 1))) & (geo.BN - 1); hp < 128; hp += geo.BN) {
@@ -634,12 +673,31 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
 #pragma unroll
       for (int mm = 0; mm < NMLP; ++mm)
         if (mm == m) { acc_s[mm] += sv; acc_q[mm] += qv; }
+      if (pool_in && !pool_full) {
+        // run that crosses the end of the graph's columns: per-pixel tests
+        float mx = pool_mx, mn = pool_mn;
+#pragma unroll 1
+        for (int k = 0; k < kPxPerPart / 8; ++k) {
+          const uint4 wv = *reinterpret_cast<const uint4*>(row + (((chunk0 + k) ^ (c & 7)) << 4));
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 f = Elem<T>::unpack2(ww[u]);
+            const int pj = pool_pj0 + 8 * k + 2 * u;
+            if (pj < pool_pj_end && (pj & (geo.BN - 1)) != geo.BN - 1) { mx = fmaxf(mx, f.x); mn = fminf(mn, f.x); }
+            if (pj + 1 < pool_pj_end && ((pj + 1) & (geo.BN - 1)) != geo.BN - 1) { mx = fmaxf(mx, f.y); mn = fminf(mn, f.y); }
+          }
+        }
+        pool_mx = mx;
+        pool_mn = mn;
+      }
       TIMING_MARK(3);
       if (st == 0) bulk_wait_group_read0();      // the store has read the staged tile (it ran under the statistics pass)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tile_empty[buf]);
       TIMING_MARK(4);
     }
+    if (pool_row >= 0) pool_flush();
     TIMING_FLUSH(16, st == 0);
     if (st == 0) bulk_wait_group0();             // every store has landed before the CTA exits
 #pragma unroll
@@ -1184,6 +1242,7 @@ struct MlpLaunch {
   int out_mode[2];
   int ones[2];
   double* stat_acc;    // [G][nmlp][COUT][2], zeroed here
+  unsigned int* rowenc[2];   // fused max pooling instead of the store (see MlpArgs), or null
 };
 
 template <typename T, int COUT, int NMLP>
@@ -1205,6 +1264,7 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
     a.out[m] = L.out[m];
     a.out_mode[m] = L.out_mode[m];
     a.ones[m] = L.ones[m];
+    a.rowenc[m] = L.rowenc[m];
   }
   a.stat_acc = L.stat_acc;
   a.n_per_graph = npg;
@@ -1230,17 +1290,28 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   }
   const size_t smem = MlpSmem<COUT, NMLP>::bytes(a.K1, a.K1g, a.depth, a.Kh);
   FGNN_CHECK_ARG(smem <= 227 * 1024, "MLP kernel needs %zu bytes of shared memory", smem);
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
+  const bool pool = a.rowenc[0] != nullptr;
+  FGNN_CHECK_ARG(!pool || NMLP == 1, "fused pooling is only built for single-MLP launches");
+  static size_t attr_bytes[2] = {0, 0};
+  if (smem > attr_bytes[pool]) {
+    if (pool) {
+      if constexpr (NMLP == 1)
+        FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+      FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    attr_bytes[pool] = smem;
   }
   FGNN_CUDA(cudaMemsetAsync(L.stat_acc, 0, (size_t)G * NMLP * COUT * 2 * sizeof(double), st));
   long total_tiles = (long)G * ((geo.PSC + kTileM - 1) / kTileM);
   int grid = (int)std::min<long>((long)num_sms(), total_tiles);
   if (grid < 1) grid = 1;
   prof::begin(prof::kMlp, st);
-  tc_mlp_kernel<T, COUT, NMLP><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+  if (pool) {
+    if constexpr (NMLP == 1) tc_mlp_kernel<T, COUT, NMLP, true><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+  } else {
+    tc_mlp_kernel<T, COUT, NMLP, false><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+  }
   prof::end(prof::kMlp, st);
   FGNN_LAUNCHED();
   return FGNN_OK;
@@ -1272,6 +1343,7 @@ struct MlpGroup {
   int ones[2];
   float* coef[2];
   double* stat_acc;
+  unsigned int* rowenc[2];   // fused max pooling of this MLP's output instead of storing it (or null)
 };
 
 template <typename T>
@@ -1306,6 +1378,7 @@ int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int3
     L.out[m] = M.out[m];
     L.out_mode[m] = M.out_mode[m];
     L.ones[m] = M.ones[m];
+    L.rowenc[m] = M.rowenc[m];
   }
   L.stat_acc = M.stat_acc;
   if (int e = launch_mlp<T>(L, G, geo, npg, st)) return e;
@@ -1377,6 +1450,7 @@ struct Buffers {
   float *bf12, *bf3;                           // folded first-layer biases
   double* stat_acc;                            // [chunk][2][C][2]
   void* wh;                                    // [blocks][3][depth-1][C][Kh]
+  unsigned int* rowenc;                        // [chunk][C][N][2] row max / min codes of the last block's output
 };
 
 size_t carve(const Plan& pl, int num_blocks, Arena& ar, Buffers& B) {
@@ -1399,6 +1473,7 @@ size_t carve(const Plan& pl, int num_blocks, Arena& ar, Buffers& B) {
   B.stat_acc = ar.take<double>(4 * nc);
   const int Kh = pl.C < 64 ? 64 : pl.C;
   B.wh = ar.take<uint16_t>((size_t)num_blocks * 3 * std::max(pl.depth_max - 1, 1) * pl.C * Kh, 1024);
+  B.rowenc = ar.take<unsigned int>(nc * pl.geo.N * 2, 1024);
   return align_up(ar.off, 1024);
 }
 
@@ -1476,6 +1551,11 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, i
         M.wh = whb + (size_t)2 * dm1 * C * Kh;
         M.out[0] = nxt; M.out_mode[0] = kOutC; M.ones[0] = 0; M.coef[0] = nxt_coef;
         M.stat_acc = B.stat_acc;
+        if (b == p.num_blocks - 1) {
+          // the last block's output is only ever max-pooled: keep its row max / min and never write the planes
+          M.rowenc[0] = B.rowenc;
+          FGNN_CUDA(cudaMemsetAsync(B.rowenc, 0, (size_t)gc * C * N * 2 * sizeof(unsigned int), st));
+        }
         if (int e = run_mlp_group<T>(M, C, gc, geo, n_c, st)) return e;
       }
       cur = nxt;
@@ -1485,7 +1565,8 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, i
       nxt_coef = (nxt_coef == B.coef3a) ? B.coef3b : B.coef3a;
     }
     const long rows = (long)gc * C * N;
-    pool_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cur, cur_coef, emb + (size_t)g0 * C * N, C, geo, rows, n_c);
+    pool_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(B.rowenc, cur_coef, emb + (size_t)g0 * C * N, C, N,
+                                                                       rows, n_c);
     FGNN_LAUNCHED();
   }
   return FGNN_OK;
