@@ -278,6 +278,9 @@ struct MlpArgs {
 };
 
 constexpr int kSlots = 4;
+// warp roles of the conv-chain CTA (15 warps).  The scheduler prefers higher warp ids: the control warps sit on top so
+// that a wake-up is served at once (epilogue warps on top instead was measured 0.8% slower).
+constexpr int kWEpi = 0, kWProd = 8, kWMma = 9, kWStat = 11;
 
 // Optional cycle accounting of the conv-chain kernel's roles (compile with -DFGNN_TC_TIMING; bring-up only).
 #ifdef FGNN_TC_TIMING
@@ -364,7 +367,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     const int c = i % COUT, ml = i / COUT;
     s_biash[i] = args.bias[ml / (depth - 2)][1 + ml % (depth - 2)][c];
   }
-  if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kWProd) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -393,7 +396,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
 
   // Warp ids: the scheduler favours higher warp ids, and the two control warps must never be starved by
   // epilogue warps polling an mbarrier on the same sub-partition -> control warps get the highest ids.
-  if (warp == 8) {
+  if (warp == kWProd) {
     if (V > 0) {
       // ================= TMA producer (whole warp, elected lane issues) =================
       if (lane == 0) {
@@ -440,11 +443,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         }
       }
     }
-  } else if (warp == 9 || warp == 10) {
+  } else if (warp == kWMma || warp == kWMma + 1) {
     // ================= MMA issuers: one warp per epilogue group (whole warp, elected lane issues) =================
     // Warp 9+e feeds the two TMEM slots of group e in that group's own item order, so a slow group never
     // blocks the other one and each issuer handles half of the tcgen05 traffic.
-    const int eg = warp - 9;
+    const int eg = warp - kWMma;
     if (V > 0) {
     const uint32_t idesc1 = make_idesc(Elem<T>::kFmt, /*A MN-major*/ 1, /*B K-major*/ 0, kTileM, COUT);
     const uint32_t idesc2 = make_idesc(Elem<T>::kFmt, 0, 0, kTileM, COUT);
@@ -537,17 +540,17 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           }
         }
       }
-      TIMING_FLUSH(0, warp == 9 && lane == 0);
+      TIMING_FLUSH(0, warp == kWMma && lane == 0);
       Walker wl = wi;                          // the producer may still wait for this group's release of later graphs
       walker_seek(wl, t_end - 1);
       release_graphs_upto(wl.g - g_first + 1);
     }
-  } else if (warp >= 11) {
+  } else if (warp >= kWStat && warp < kWStat + 4) {
     // ================= statistics warps (11-14): sum / sum of squares per channel from the staged tile ==========
     // thread -> (channel c, part): `part` selects a run of kPxPerPart consecutive pixels of the 128-pixel tile
     constexpr int kParts = 128 / COUT;             // 2 for COUT = 64, 4 for COUT = 32
     constexpr int kPxPerPart = 128 / kParts;       // 64 / 32 pixels = 8 / 4 16-byte chunks of one 64-pixel half
-    const int st = threadIdx.x - 352;              // 0..127
+    const int st = threadIdx.x - kWStat * 32;              // 0..127
     const int c = st % COUT, part = st / COUT;
     const int half = (part * kPxPerPart) / 64, chunk0 = ((part * kPxPerPart) % 64) / 8;
     float acc_s[NMLP], acc_q[NMLP];
@@ -705,14 +708,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   } else {
     // ================= epilogue groups (warps 0-3 / 4-7) =================
     // Each group owns two TMEM slots; its own MMA-issuing warp (9 + group) feeds them.
-    const int eg = warp / 4;                 // 0: slots 0,2   1: slots 1,3
+    const int eg = (warp - kWEpi) / 4;                 // 0: slots 0,2   1: slots 1,3
     const int quad = warp % 4;               // TMEM lane quadrant this warp may access
     const int pix_in_tile = quad * 32 + lane;
     uint32_t ph_mma = 0;                     // phase bits of mma_done[s]
     int n_final = 0;                         // final-layer items this group has produced (staging buffer = n_final & 1)
     Walker w;
     walker_init(w);
-    const int et = threadIdx.x - eg * 128;   // thread index inside the group
+    const int et = threadIdx.x - kWEpi * 32 - eg * 128;   // thread index inside the group
     int bias_g0 = -1, bias_g1 = -1;          // graph whose folded first-layer bias sits in s_bias1[slot]
     int slot_g0 = 0, slot_g1 = 0, slot_n0 = 0, slot_n1 = 0;   // (graph, its n, first tile of graph) of the tile in this group's two slots
     long slot_base0 = 0, slot_base1 = 0;
@@ -860,12 +863,12 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         }
       }
     }
-    TIMING_FLUSH(8, warp == 2 && lane == 0);
+    TIMING_FLUSH(8, warp == kWEpi + 2 && lane == 0);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) {
+  if (warp == kWProd) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
   }
