@@ -213,3 +213,28 @@ def test_bench_sized_launches_are_stable():
         for i in (0, G - 1):
             solo = model.node_embedder.forward_fused(x[i:i + 1], "bf16")
             assert rel_fro(solo[0].cpu(), first[i].cpu()) < 1e-1
+
+
+def test_ragged_large_sizes_match_fp32_path():
+    """cfg4-like ragged batch (n from 50 to 1000, width 64, 4 blocks): beyond the CPU oracle in test time, so the
+    fp16 tensor-core embedder is checked against the fp32 CUDA path (itself golden-tested) graph by graph; padding
+    rows must be exactly zero (the fused pooling only ever touches rows < n)."""
+    gen = torch.Generator().manual_seed(4242)
+    sizes = [1000, 333, 50, 640, 128, 129]
+    c = 64
+    sd = O.xavier_state_dict(2, c, 4, 3, gen)
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=4,
+                    in_features=c, out_features=c, depth_of_mlp=3, constant_n_vertices=False)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    graphs = [O.synthetic_pair(s, 0.2, 0.1, gen)[0] for s in sizes]
+    x = mt.from_list(graphs, dims=(1, 2)).to(DEV)
+    with torch.no_grad():
+        ref = model.node_embedder.forward_fused(x, "fp32").tensor.rename(None).cpu()
+        e = model.node_embedder.forward_fused(x, "fp16").tensor.rename(None).cpu()
+    for i, s in enumerate(sizes):
+        err = rel_fro(e[i, :, :s], ref[i, :, :s])
+        print(f"ragged n={s}: fp16 vs fp32 path rel err {err:.3e}")
+        assert err < EMB_TOL["fp16"]
+        assert float(e[i, :, s:].abs().sum()) == 0
