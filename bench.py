@@ -230,17 +230,35 @@ def main():
     x2_ready = torch.cuda.Event()
     x2_free = torch.cuda.Event()
     x2_free.record()
+    # e2e input pipeline (what a loader does): both H2D copies of a step run on a side stream.  x2 is copied under the
+    # first embedder pass of the same step; x1 of the NEXT step is copied under the second pass into the other of two
+    # device buffers.  The first step of a run copies its own x1 on the main stream (exposed), so every step's inputs
+    # are copied from pinned host memory inside the timed region.
+    x1_bufs = [x1_d, torch.empty_like(x1_d)]
+    x1_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    x1_free = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in x1_free:
+        ev.record()
+    pipe = {"k": 0, "primed": False}
 
     def step_e2e():
-        # H2D of both graph batches from pinned host memory; the second copy runs on a side stream and
-        # overlaps the first embedder pass (still inside the timed region, every step)
         main = torch.cuda.current_stream(dev)
-        x1_d.copy_(x1_h, non_blocking=True)
+        cur = pipe["k"] & 1
+        nxt = cur ^ 1
+        if not pipe["primed"]:
+            x1_bufs[cur].copy_(x1_h, non_blocking=True)
+            pipe["primed"] = True
+        else:
+            main.wait_event(x1_ready[cur])
         copy_stream.wait_event(x2_free)              # previous step's reads of x2_d are done
         with torch.cuda.stream(copy_stream):
             x2_d.copy_(x2_h, non_blocking=True)
             x2_ready.record(copy_stream)
-        e1 = model.embed({"input": x1_d})
+            copy_stream.wait_event(x1_free[nxt])     # the step before last has finished reading that buffer
+            x1_bufs[nxt].copy_(x1_h, non_blocking=True)
+            x1_ready[nxt].record(copy_stream)
+        e1 = model.embed({"input": x1_bufs[cur]})
+        x1_free[cur].record(main)
         main.wait_event(x2_ready)
         e2 = model.embed({"input": x2_d})
         x2_free.record(main)
@@ -248,6 +266,7 @@ def main():
         ce, correct = _ops.CrossEntropyIdentityFunction.apply(scores, None)
         res = torch.stack((ce.sum() / (pairs * cfg["n"]), correct.sum().float()))
         res_h.copy_(res, non_blocking=False)       # device -> host read of loss and #correct
+        pipe["k"] += 1
         return res_h
 
     def barrier():
@@ -296,6 +315,8 @@ def main():
         # ---- end-to-end timed region ----
         for _ in range(2):
             step_e2e()
+        torch.cuda.synchronize(dev)
+        pipe["primed"] = False                       # the timed run starts with an exposed copy of its own first input
         ms_e2e = timed(step_e2e, args.steps)
 
     if rank != 0:
@@ -356,7 +377,9 @@ def main():
         "roofline": roofline,
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(x1_h.numel() * 4 * 2), "d2h_bytes_per_step": int(res_h.numel() * 4)},
+                "h2d_bytes_per_step": int(x1_h.numel() * 4 * 2), "d2h_bytes_per_step": int(res_h.numel() * 4),
+                "pipeline": "H2D on a side stream: x2 under this step's first embedder pass, next step's x1 under the "
+                            "second (double-buffered); the run's first step copies its own x1 exposed"},
     }
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sec = cpu_reference_rate(cfg, steps=2, warmup=1)
