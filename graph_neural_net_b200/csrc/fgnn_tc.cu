@@ -249,12 +249,18 @@ __global__ void finalize_coef_kernel(CoefArgs a, int total) {
 //           consume the same staged input tile ("virtual tiles" v = tile * NMLP + m)
 //   layer1: D[128 px, COUT] = X[px, K1] * W1f[g][m]^T   A = TMA-staged smem (MN-major), B = smem (K-major)
 //   layer>=2: D = relu(D + b) (16-bit, written back to TMEM) * W^T        A = TMEM, B = smem
-//   output: raw last-layer accumulators as 16-bit planes (the last bias cancels in GraphNorm), their
-//           per-(graph, channel) sum and sum of squares (fp32 in registers, double atomics per flush).
-// Warp roles: warps 0-3 / 4-7 two epilogue groups, warp 8 TMA producer, warps 9-10 MMA issuers (one per group),
-// warps 11-14 GraphNorm statistics; the groups
-// alternate virtual tiles (slot parity).  TMEM slot s: accumulator columns [s*1.5*COUT, +COUT),
-// packed hidden activations in the next COUT/2 columns.
+//   output: raw last-layer accumulators as 16-bit planes (the last bias cancels in GraphNorm): staged in shared
+//           memory with stmatrix.trans (16x256b accumulator fragments), stored by TMA; their per-(graph, channel)
+//           sum and sum of squares are taken from the staged tile by the statistics warps (fp32 partials per
+//           thread, double atomics on a graph change).  POOL = true (last block): the tile is not stored, the
+//           statistics warps also publish the row-wise max / min for the fused column-max pooling.
+// Warp roles (kWEpi / kWProd / kWMma / kWStat): warps 0-3 / 4-7 two epilogue groups, warp 8 TMA producer,
+// warps 9-10 MMA issuers (one per group), warps 11-14 GraphNorm statistics + TMA store; the groups alternate
+// virtual tiles (slot parity).  TMEM slot s: accumulator columns [s*1.5*COUT, +COUT), packed hidden activations
+// in the next COUT/2 columns.
+// Barrier rule: a waiter sees ONE parity bit of an mbarrier, so no waiter may skip a phase.  With NMLP = 1 the
+// two MMA warps consume alternate tiles of the input ring; each also observes the other's tile and releases its
+// stage (in_empty counts two arrivals).
 // =============================================================================================
 enum OutMode { kOutC = 0, kOutA = 1, kOutB = 2 };   // output plane layout: rows i / i + i/127 / i + i/(BN-1)
 
@@ -546,7 +552,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       release_graphs_upto(wl.g - g_first + 1);
     }
   } else if (warp >= kWStat && warp < kWStat + 4) {
-    // ================= statistics warps (11-14): sum / sum of squares per channel from the staged tile ==========
+    // ================= statistics warps (kWStat .. +3): sum / sum of squares per channel from the staged tile ======
     // thread -> (channel c, part): `part` selects a run of kPxPerPart consecutive pixels of the 128-pixel tile
     constexpr int kParts = 128 / COUT;             // 2 for COUT = 64, 4 for COUT = 32
     constexpr int kPxPerPart = 128 / kParts;       // 64 / 32 pixels = 8 / 4 16-byte chunks of one 64-pixel half
@@ -847,7 +853,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
             if (lane == 0) mbar_arrive(&h_ready[s]);
             fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tile_full[buf]);   // 4 warps; the statistics warps store the tile and reduce it
+            if (lane == 0) mbar_arrive(&tile_full[buf]);   // 4 arrivals; the statistics warps store the tile and reduce it
             ++n_final;
             // ones rows of Y1 (layout A): the last logical row of every 127-row matmul tile writes the row below it
             if (mode == kOutA && args.ones[m] && in_plane && pi < n) {
@@ -1704,7 +1710,7 @@ void dump_timing() {
       {"loop/index", "wait mma_done", "hidden epilogue", "final: index + wait tile_empty", "final: tmem ld + cvt + stmatrix",
        "final: fences + arrive"},
       {"loop", "index + stat flush", "wait tile_full", "TMA store issue + reduce", "wait store read + arrive", "-"}};
-  const char* role[3] = {"MMA issuer (warp 9)", "epilogue warp 2", "statistics thread 352"};
+  const char* role[3] = {"MMA issuer (warp kWMma)", "epilogue warp 2", "first statistics thread"};
   for (int r = 0; r < 3; ++r) {
     unsigned long long tot = 0;
     for (int i = 0; i < 6; ++i) tot += h[8 * r + i];
