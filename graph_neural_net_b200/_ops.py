@@ -257,6 +257,24 @@ def graphnorm_fwd(x: torch.Tensor, n_dev, gn_w, gn_b, eps: float) -> torch.Tenso
     return y
 
 
+def features_from_adjacency(adj: torch.Tensor, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batch of adjacency matrices (G,N,N) uint8/bool on the GPU -> padded (G,2,N,N) float32 features
+    B[0]=W, B[1]=diag(W.sum(1)) (reference loaders/data_generator.py:118-125 + maskedtensor.from_list padding)."""
+    lib = L.get_lib()
+    if not adj.is_cuda:
+        raise L.FgnnError("adjacency must be a CUDA tensor (there is no CPU fallback)")
+    if adj.dtype == torch.bool:
+        adj = adj.view(torch.uint8)
+    if adj.dtype != torch.uint8 or adj.dim() != 3 or adj.shape[1] != adj.shape[2]:
+        raise L.FgnnError("adjacency must be (G,N,N) uint8 or bool")
+    adj = adj.contiguous()
+    G, N, _ = adj.shape
+    out = torch.empty((G, 2, N, N), device=adj.device, dtype=torch.float32)
+    L.check(lib.fgnn_features_from_adjacency_u8(L.ptr(adj), L.ptr(out), G, N, _npg(n_dev), L.stream_ptr(adj.device)),
+            "fgnn_features_from_adjacency_u8")
+    return out
+
+
 def embed_fwd(params: L.EmbedParams, precision: int, x: torch.Tensor, c_out: int,
               n_dev: Optional[torch.Tensor], n_host: Optional[List[int]]) -> torch.Tensor:
     """Fused node_embedding forward: x (G,c_in,N,N) -> (G,C,N)."""

@@ -197,6 +197,13 @@ int fgnn_matmul_bwd_f32(const float* a, const float* b, const float* dout, float
   return FGNN_OK;
 }
 
+int fgnn_features_from_adjacency_u8(const uint8_t* adj, float* out, int32_t G, int32_t N, const int32_t* n_per_graph,
+                                    void* stream) {
+  FGNN_CHECK_ARG(adj && out, "null pointer");
+  FGNN_CHECK_ARG(G >= 0 && N > 0, "bad shape G=%d N=%d", G, N);
+  return f32::features_from_adjacency(adj, out, G, N, n_per_graph, (cudaStream_t)stream);
+}
+
 int fgnn_colmax_fwd_f32(const float* x, float* out, int32_t* argmax, int32_t G, int32_t C, int32_t N,
                         const int32_t* n_per_graph, void* stream) {
   return f32::colmax_fwd(x, out, argmax, G, C, N, n_per_graph, (cudaStream_t)stream);

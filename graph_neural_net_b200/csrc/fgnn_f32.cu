@@ -626,6 +626,38 @@ int ce_bwd(const float* scores, const float* row_lse, const float* coef, float* 
   return FGNN_OK;
 }
 
+// adjacency (uint8) -> (W, diag(deg)) features, one warp per row  (loaders/data_generator.py:118-125)
+__global__ void __launch_bounds__(256)
+features_from_adjacency_kernel(const uint8_t* __restrict__ adj, float* __restrict__ out, int N, long rows,
+                               const int32_t* __restrict__ n_per_graph) {
+  const long row = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const int g = (int)(row / N), i = (int)(row % N);
+  const int n = n_per_graph ? n_per_graph[g] : N;
+  const uint8_t* a = adj + ((long)g * N + i) * N;
+  float* w = out + (((long)g * 2) * N + i) * N;
+  float* d = out + (((long)g * 2 + 1) * N + i) * N;
+  int deg = 0;
+  for (int j = lane; j < N; j += 32) {
+    const int v = (i < n && j < n) ? (a[j] != 0) : 0;
+    deg += v;
+    w[j] = (float)v;
+    d[j] = 0.f;
+  }
+  for (int o = 16; o > 0; o >>= 1) deg += __shfl_xor_sync(0xffffffffu, deg, o);
+  __syncwarp();
+  if (lane == 0 && i < n) d[i] = (float)deg;
+}
+
+int features_from_adjacency(const uint8_t* adj, float* out, int G, int N, const int32_t* n_per_graph, cudaStream_t st) {
+  const long rows = (long)G * N;
+  if (rows == 0) return FGNN_OK;
+  features_from_adjacency_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(adj, out, N, rows, n_per_graph);
+  FGNN_LAUNCHED();
+  return FGNN_OK;
+}
+
 int concat_channels(const float* a, const float* b, float* out, int G, int Ca, int Cb, int N,
                     cudaStream_t st) {
   long P = (long)N * N;

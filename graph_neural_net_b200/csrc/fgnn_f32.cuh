@@ -38,5 +38,8 @@ int ce_bwd(const float* scores, const float* row_lse, const float* coef, float* 
 int concat_channels(const float* a, const float* b, float* out, int G, int Ca, int Cb, int N,
                     cudaStream_t st);
 
+// (G,N,N) uint8 adjacency -> (G,2,N,N) features W, diag(deg)  (loaders/data_generator.py:118-125)
+int features_from_adjacency(const uint8_t* adj, float* out, int G, int N, const int32_t* n_per_graph, cudaStream_t st);
+
 }  // namespace f32
 }  // namespace fgnn

@@ -123,6 +123,14 @@ int fgnn_colmax_fwd_f32(const float* x, float* out, int32_t* argmax, int32_t G, 
 int fgnn_colmax_bwd_f32(const float* dout, const int32_t* argmax, float* dx, int32_t G, int32_t C,
                         int32_t N, const int32_t* n_per_graph, void* stream);
 
+/* Input construction on the device: adjacency_matrix_to_tensor_representation
+ * (loaders/data_generator.py:118-125) followed by the zero padding of maskedtensor.from_list
+ * (maskedtensors/maskedtensor.py:8-48) for a whole batch.  adj (G,N,N) uint8 in {0,1}, row-major, only the
+ * leading n_g x n_g block of graph g is read; out (G,2,N,N) float32: out[g,0] = W, out[g,1] = diag(W.sum(1)),
+ * zero outside the n_g x n_g block.  Ships 1 byte per entry over PCIe instead of 8. */
+int fgnn_features_from_adjacency_u8(const uint8_t* adj, float* out, int32_t G, int32_t N,
+                                    const int32_t* n_per_graph, void* stream);
+
 /* Siamese head: scores[g] = e1[g]^T e2[g]  (models/trainers.py:67).  e1,e2 (G,C,N) -> (G,N,N). */
 int fgnn_scores_fwd_f32(const float* e1, const float* e2, float* scores, int32_t G, int32_t C,
                         int32_t N, const int32_t* n_per_graph, void* stream);

@@ -188,3 +188,26 @@ def test_fp32_train_step_reduces_loss():
     losses = [train_step(model, opt, {"input": x1}, {"input": x2})[0] for _ in range(8)]
     assert abs(losses[0] - float(z["loss_mean"])) < 1e-4
     assert losses[-1] < losses[0]
+
+
+def test_features_from_adjacency_matches_reference_representation():
+    """input construction on the device == the reference's host construction + padding."""
+    from graph_neural_net_b200.loaders import data_generator as dg
+    gen = torch.Generator().manual_seed(5)
+    sizes = [37, 64, 5, 50]
+    N = max(sizes)
+    adj = torch.zeros((len(sizes), N, N), dtype=torch.uint8)
+    graphs = []
+    for g, n in enumerate(sizes):
+        W = (torch.rand((n, n), generator=gen) < 0.3)
+        W = torch.triu(W, 1)
+        W = (W | W.T)
+        adj[g, :n, :n] = W.to(torch.uint8)
+        graphs.append(O.adjacency_to_features(W.float()))
+    # garbage outside the n x n blocks must be ignored
+    adj[0, 40:, :] = 1
+    ref = mt.from_list(graphs, dims=(1, 2)).tensor.rename(None)
+    out = dg.adjacency_batch_to_tensor_representation(adj.to(DEV), torch.tensor(sizes, dtype=torch.int32, device=DEV))
+    assert torch.equal(out.cpu(), ref)
+    dense = dg.adjacency_batch_to_tensor_representation(adj[1:2, :64, :64].contiguous().to(DEV))
+    assert torch.equal(dense[0].cpu(), graphs[1])
