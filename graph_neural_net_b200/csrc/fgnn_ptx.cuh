@@ -378,6 +378,19 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 
 // ---- 16-bit element helpers ----------------------------------------------------------------------
+// 16-byte load from a SHARED-space address.  A `const float*` that may point to one of several shared arrays is a
+// generic pointer to the compiler, which then emits LD.E (generic) instead of LDS; volatile so that it is neither
+// hoisted over the barrier that publishes the data nor merged with another load.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
 template <typename T> struct Elem;
 // packed fp32x2 add (Blackwell FADD2) and fused relu + round + pack to a 16-bit pair
 __device__ __forceinline__ void add2(float& a, float& b, float c, float d) {

@@ -619,6 +619,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         bulk_commit_group();
       }
       const uint8_t* row = s_out + (size_t)buf * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
+      const uint32_t row_s = smem_u32(row);          // explicit shared-space loads: `smem` is a generic pointer to the compiler
       float sv = 0.f, qv = 0.f;
       // fused pooling (see below): position of this thread's run, and whether all of it lies inside the graph
       const int pstart = p0 + part * kPxPerPart;
@@ -636,7 +637,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;    // even / odd pixels, packed fp32x2 arithmetic
 #pragma unroll
         for (int k = 0; k < kPxPerPart / 8; ++k) {
-          const uint4 wv = *reinterpret_cast<const uint4*>(row + (((chunk0 + k) ^ (c & 7)) << 4));
+          const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
           const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -653,7 +654,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, mx = pool_mx, mn = pool_mn;
 #pragma unroll
         for (int k = 0; k < kPxPerPart / 8; ++k) {
-          const uint4 wv = *reinterpret_cast<const uint4*>(row + (((chunk0 + k) ^ (c & 7)) << 4));
+          const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
           const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -687,7 +688,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         float mx = pool_mx, mn = pool_mn;
 #pragma unroll 1
         for (int k = 0; k < kPxPerPart / 8; ++k) {
-          const uint4 wv = *reinterpret_cast<const uint4*>(row + (((chunk0 + k) ^ (c & 7)) << 4));
+          const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
           const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -763,21 +764,26 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           if (!last) {
             const float* bias = (l == 0) ? (s_bias1 + s * COUT) : (s_biash + (m * (depth - 2) + (l - 1)) * COUT);
             {
-              // all accumulator columns in flight at once: one TMEM round trip per item instead of one per 32 columns
+              // all accumulator columns in flight at once: one TMEM round trip per item instead of one per 32 columns;
+              // the biases of the first 32 columns are fetched from shared memory while that load is in flight, the
+              // others once the first half's registers are free (a single exposed LDS latency per pass)
+              const uint32_t bias_s = smem_u32(bias);
               uint32_t r[COUT];
 #pragma unroll
               for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld32(lane_addr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
-              tmem_wait_ld();
 #pragma unroll
               for (int c0 = 0; c0 < COUT; c0 += 32) {
+                float4 bq[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) bq[u] = lds128(bias_s + (uint32_t)(c0 + 4 * u) * 4u);
+                if (c0 == 0) tmem_wait_ld();
                 uint32_t h[16];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + 4 * u);
                   float x0 = __uint_as_float(r[c0 + 4 * u]), x1 = __uint_as_float(r[c0 + 4 * u + 1]);
                   float x2 = __uint_as_float(r[c0 + 4 * u + 2]), x3 = __uint_as_float(r[c0 + 4 * u + 3]);
-                  add2(x0, x1, b4.x, b4.y);
-                  add2(x2, x3, b4.z, b4.w);
+                  add2(x0, x1, bq[u].x, bq[u].y);
+                  add2(x2, x3, bq[u].z, bq[u].w);
                   h[2 * u] = Elem<T>::pack_relu(x0, x1);
                   h[2 * u + 1] = Elem<T>::pack_relu(x2, x3);
                 }
