@@ -324,7 +324,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   constexpr int kSlotW = COUT * 3 / 2;
   constexpr uint32_t kTmemCols = (kSlots * kSlotW <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // round the base up to 1024 bytes with POINTER arithmetic: an integer round trip makes the compiler treat everything
+  // behind it as generic memory (LD.E / ST.E instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int K1 = args.K1, K1g = args.K1g, depth = args.depth, Kh = args.Kh;
   const Geo geo = args.geo;
   const uint32_t stage_bytes = (uint32_t)K1 * 256u;
