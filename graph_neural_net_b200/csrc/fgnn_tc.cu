@@ -606,18 +606,17 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       mbar_wait(&tile_full[buf], (uint32_t)(kb >> 1) & 1u);
       TIMING_MARK(2);
       constexpr bool pooled = POOL;                      // compile-time: the non-pooled kernels carry none of this
-      if (st == 0 && !pooled) {
+      const bool storer = !pooled && lane == 0 && warp < kWStat + 2;   // lane 0 of the first two statistics warps: one half each
+      if (storer) {
         // the four epilogue warps have staged the tile and fenced it for the async proxy: store it (one 64-pixel
         // half per TMA; a half never straddles a row because NPC % 64 == 0)
         const CUtensorMap* mo = (m == 0) ? &map_o0 : &map_o1;
         const int mode = args.out_mode[m];
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int ph = p0 + hf * 64;
-          const int prw = ph / geo.NPC, col = ph - prw * geo.NPC;
-          const int prow = (mode == kOutA) ? prw + prw / kTM1 : (mode == kOutB ? prw + prw / geo.TN1 : prw);
-          if (prw < geo.N) tma_store_3d(mo, s_out + (size_t)buf * (COUT * 256) + (size_t)hf * (COUT * 128), col, prow, g * COUT);
-        }
+        const int hf = warp - kWStat;
+        const int ph = p0 + hf * 64;
+        const int prw = ph / geo.NPC, col = ph - prw * geo.NPC;
+        const int prow = (mode == kOutA) ? prw + prw / kTM1 : (mode == kOutB ? prw + prw / geo.TN1 : prw);
+        if (prw < geo.N) tma_store_3d(mo, s_out + (size_t)buf * (COUT * 256) + (size_t)hf * (COUT * 128), col, prow, g * COUT);
         bulk_commit_group();
       }
       const uint8_t* row = s_out + (size_t)buf * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
@@ -704,14 +703,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         pool_mn = mn;
       }
       TIMING_MARK(3);
-      if (st == 0) bulk_wait_group_read0();      // the store has read the staged tile (it ran under the statistics pass)
+      if (storer) bulk_wait_group_read0();       // the store has read the staged tile (it ran under the statistics pass)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tile_empty[buf]);
       TIMING_MARK(4);
     }
     if (pool_row >= 0) pool_flush();
     TIMING_FLUSH(16, st == 0);
-    if (st == 0) bulk_wait_group0();             // every store has landed before the CTA exits
+    if (lane == 0 && warp < kWStat + 2) bulk_wait_group0();   // every store has landed before the CTA exits
 #pragma unroll
     for (int mm = 0; mm < NMLP; ++mm) flush(mm);
   } else {
