@@ -295,3 +295,27 @@ def embed_fwd(params: L.EmbedParams, precision: int, x: torch.Tensor, c_out: int
                                C.cast(nh, C.c_void_p) if nh is not None else None, L.ptr(ws), ws.numel(),
                                L.stream_ptr(x.device)), "fgnn_embed_fwd")
     return emb
+
+
+def embed_fwd_adjacency(params: L.EmbedParams, precision: int, adj: torch.Tensor, c_out: int,
+                        n_dev: Optional[torch.Tensor]) -> torch.Tensor:
+    """Fused node_embedding forward fed from a (G,N,N) uint8/bool adjacency batch (16-bit precisions only): the
+    input features W, diag(deg) are built on the device directly in the kernels' plane layout."""
+    lib = L.get_lib()
+    if not adj.is_cuda:
+        raise L.FgnnError("adjacency must be a CUDA tensor (there is no CPU fallback)")
+    if adj.dtype == torch.bool:
+        adj = adj.view(torch.uint8)
+    if adj.dtype != torch.uint8 or adj.dim() != 3 or adj.shape[1] != adj.shape[2]:
+        raise L.FgnnError("adjacency must be (G,N,N) uint8 or bool")
+    adj = adj.contiguous()
+    G, N, _ = adj.shape
+    emb = torch.empty((G, c_out, N), device=adj.device, dtype=torch.float32)
+    nbytes = lib.fgnn_embed_workspace_bytes(C.byref(params), precision, G, N)
+    if nbytes == 0:
+        raise L.FgnnError("fgnn_embed_workspace_bytes returned 0: " + lib.fgnn_last_error().decode())
+    ws = L.workspace(adj.device, nbytes)
+    L.check(lib.fgnn_embed_fwd_adjacency_u8(C.byref(params), precision, L.ptr(adj), L.ptr(emb), G, N, _npg(n_dev),
+                                            L.ptr(ws), ws.numel(), L.stream_ptr(adj.device)),
+            "fgnn_embed_fwd_adjacency_u8")
+    return emb

@@ -262,6 +262,15 @@ int fgnn_embed_fwd(const fgnn_embed_params* p, int32_t precision, const float* x
   return fail(FGNN_ERR_INVALID, "unknown precision %d", precision);
 }
 
+int fgnn_embed_fwd_adjacency_u8(const fgnn_embed_params* p, int32_t precision, const uint8_t* adj, float* emb,
+                                int32_t G, int32_t N, const int32_t* n_per_graph, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (int e = check_embed(p, G, N)) return e;
+  FGNN_CHECK_ARG(adj && emb && workspace, "null pointer");
+  return tc::embed_fwd_adjacency(*p, precision, adj, emb, G, N, n_per_graph, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
+}
+
 size_t fgnn_debug_tc_matmul_workspace_bytes(int32_t G, int32_t C, int32_t N) {
   return tc::debug_matmul_workspace_bytes(G, C, N);
 }

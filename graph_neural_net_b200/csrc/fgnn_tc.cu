@@ -112,6 +112,36 @@ __global__ void to_planes_kernel(const float* __restrict__ x, T* __restrict__ ou
   }
 }
 
+// uint8 adjacency (G,N,N) -> the two layout-C input planes of block 1: channel 0 = W, channel 1 = diag(W.sum(1))
+// (loaders/data_generator.py:118-125 without materialising the fp32 (G,2,N,N) tensor).  One warp per plane row;
+// values are 0/1 and integer degrees <= N <= 1024 (exact in fp16; bf16 rounds degrees above 256 exactly as
+// to_planes_kernel does on the fp32 features).
+template <typename T>
+__global__ void __launch_bounds__(256)
+adjacency_to_planes_kernel(const uint8_t* __restrict__ adj, T* __restrict__ out, Geo geo, long rows,
+                           const int32_t* __restrict__ n_per_graph) {
+  const long row = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const int g = (int)(row / geo.N), i = (int)(row % geo.N);
+  const int n = graph_n(n_per_graph, g, geo.N);
+  const uint8_t* a = adj + ((long)g * geo.N + i) * geo.N;
+  T* w = out + ((long)g * 2) * geo.PSC + (long)i * geo.NPC;
+  T* d = w + geo.PSC;
+  int deg = 0;
+  for (int pj = lane; pj < geo.NPC; pj += 32) {
+    const bool hole = (pj & (geo.BN - 1)) == geo.BN - 1;
+    const int j = pj - (pj >> geo.BNLOG);
+    const int v = (!hole && i < n && j < n) ? (a[j] != 0) : 0;
+    deg += v;
+    w[pj] = Elem<T>::from_float((float)v);
+    d[pj] = Elem<T>::from_float(0.f);
+  }
+  for (int o = 16; o > 0; o >>= 1) deg += __shfl_xor_sync(0xffffffffu, deg, o);
+  __syncwarp();
+  if (lane == 0 && i < n) d[i + i / geo.TN1] = Elem<T>::from_float((float)deg);
+}
+
 // zero the hole rows of layout-B planes (the conv kernel never writes them; they must contribute 0 to K sums)
 template <typename T>
 __global__ void zero_hole_rows_kernel(T* __restrict__ y, Geo geo) {
@@ -1494,8 +1524,8 @@ size_t carve(const Plan& pl, int num_blocks, Arena& ar, Buffers& B) {
 }
 
 template <typename T>
-int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, int N, const int32_t* npg, void* ws,
-                size_t ws_bytes, cudaStream_t st) {
+int embed_fwd_t(const fgnn_embed_params& p, const float* x, const uint8_t* adj, float* emb, int G, int N,
+                const int32_t* npg, void* ws, size_t ws_bytes, cudaStream_t st) {
   Plan pl;
   if (int e = make_plan(p, G, N, pl)) return e;
   Arena ar(ws, ws_bytes);
@@ -1522,7 +1552,12 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, float* emb, int G, i
   for (int g0 = 0; g0 < G; g0 += pl.chunk) {
     const int gc = std::min(pl.chunk, G - g0);
     const int32_t* n_c = npg ? npg + g0 : nullptr;
-    {
+    if (adj) {
+      const long rows = (long)gc * N;
+      adjacency_to_planes_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(adj + (size_t)g0 * N * N,
+                                                                                reinterpret_cast<T*>(B.xin), geo, rows, n_c);
+      FGNN_LAUNCHED();
+    } else {
       dim3 grid((unsigned)std::min<long>(64, (geo.PSC + 255) / 256), gc * pl.cin0);
       to_planes_kernel<T><<<grid, 256, 0, st>>>(x + (size_t)g0 * pl.cin0 * N * N, reinterpret_cast<T*>(B.xin), pl.cin0,
                                                 geo, 0, n_c);
@@ -1604,8 +1639,20 @@ int embed_fwd(const fgnn_embed_params& p, int precision, const float* x, float* 
   if (!fgnn_device_supports_tcgen05())
     return fail(FGNN_ERR_UNSUPPORTED, "FGNN_BF16/FGNN_FP16 need an sm_100 device (tcgen05); there is no fallback");
   if (reinterpret_cast<uintptr_t>(ws) & 1023) return fail(FGNN_ERR_INVALID, "workspace must be 1024-byte aligned");
-  if (precision == FGNN_BF16) return embed_fwd_t<__nv_bfloat16>(p, x, emb, G, N, n_per_graph, ws, ws_bytes, st);
-  return embed_fwd_t<__half>(p, x, emb, G, N, n_per_graph, ws, ws_bytes, st);
+  if (precision == FGNN_BF16) return embed_fwd_t<__nv_bfloat16>(p, x, nullptr, emb, G, N, n_per_graph, ws, ws_bytes, st);
+  return embed_fwd_t<__half>(p, x, nullptr, emb, G, N, n_per_graph, ws, ws_bytes, st);
+}
+
+int embed_fwd_adjacency(const fgnn_embed_params& p, int precision, const uint8_t* adj, float* emb, int G, int N,
+                        const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!fgnn_device_supports_tcgen05())
+    return fail(FGNN_ERR_UNSUPPORTED, "FGNN_BF16/FGNN_FP16 need an sm_100 device (tcgen05); there is no fallback");
+  if (reinterpret_cast<uintptr_t>(ws) & 1023) return fail(FGNN_ERR_INVALID, "workspace must be 1024-byte aligned");
+  FGNN_CHECK_ARG(p.num_blocks >= 1 && p.block[0].mlp1.c_in == 2,
+                 "the adjacency input builds exactly the reference's 2 features (W, diag(deg))");
+  if (precision == FGNN_BF16) return embed_fwd_t<__nv_bfloat16>(p, nullptr, adj, emb, G, N, n_per_graph, ws, ws_bytes, st);
+  if (precision == FGNN_FP16) return embed_fwd_t<__half>(p, nullptr, adj, emb, G, N, n_per_graph, ws, ws_bytes, st);
+  return fail(FGNN_ERR_INVALID, "fgnn_embed_fwd_adjacency_u8 supports FGNN_BF16 / FGNN_FP16 (for FGNN_FP32 build the features with fgnn_features_from_adjacency_u8)");
 }
 
 // ---- debug: one tensor-core matmul on fp32 host-layout tensors ---------------------------------

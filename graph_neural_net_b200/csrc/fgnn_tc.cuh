@@ -10,6 +10,9 @@ int embed_fwd(const fgnn_embed_params& p, int precision, const float* x, float* 
               const int32_t* n_per_graph, const int32_t* n_per_graph_host, void* ws, size_t ws_bytes,
               cudaStream_t st);
 
+int embed_fwd_adjacency(const fgnn_embed_params& p, int precision, const uint8_t* adj, float* emb, int G, int N,
+                        const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
+
 size_t debug_matmul_workspace_bytes(int G, int C, int N);
 int debug_matmul(int precision, const float* a, const float* b, float* out, int G, int C, int N,
                  const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);

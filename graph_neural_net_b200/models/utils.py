@@ -169,6 +169,21 @@ class Network(nn.Module):
             return rewrap(emb, x.tensor.names[:-1])
         return emb
 
+    def forward_fused_adjacency(self, adj, precision=None, sizes=None):
+        """Embeddings straight from a CUDA (B,N,N) uint8/bool adjacency batch (`sizes`: optional CUDA int32 vertex
+        counts of a padded ragged batch) -- the reference's input construction (loaders/data_generator.py:118-125)
+        happens on the device.  16-bit precisions only; returns the plain (B,C,N) tensor."""
+        if self._fused is None:
+            raise L.FgnnError("this Network is not a node_embedding DAG; fused execution unavailable")
+        prec_name = precision or self.precision
+        if prec_name == 'fp32':
+            raise L.FgnnError("forward_fused_adjacency needs precision 'bf16' or 'fp16' "
+                              "(for fp32 build the features with loaders.data_generator.adjacency_batch_to_tensor_representation)")
+        keep = []
+        params = self._embed_params(keep)
+        c_out = self._fused[2][-1][2].convs[-1].weight.shape[0]
+        return _ops.embed_fwd_adjacency(params, L.PRECISIONS[prec_name], adj, c_out, sizes)
+
     # ---- reference-compatible execution ----------------------------------------------------------
     def forward(self, inputs):
         outputs = dict(inputs)

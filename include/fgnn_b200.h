@@ -167,6 +167,13 @@ int fgnn_embed_fwd(const fgnn_embed_params* p, int32_t precision, const float* x
                    const int32_t* n_per_graph_host, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* Same embedder fed from a uint8 adjacency batch (G,N,N) instead of the fp32 (G,2,N,N) features: the two
+ * input planes W and diag(W.sum(1)) (loaders/data_generator.py:118-125) are built on the device straight into
+ * the 16-bit plane layout.  FGNN_BF16 / FGNN_FP16 only; workspace as for fgnn_embed_fwd. */
+int fgnn_embed_fwd_adjacency_u8(const fgnn_embed_params* p, int32_t precision, const uint8_t* adj, float* emb,
+                                int32_t G, int32_t N, const int32_t* n_per_graph, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 /* Number of kernels the last call on this thread launched (bench.py's gpu_launches). */
 int64_t fgnn_launch_count(void);
 void fgnn_reset_launch_count(void);

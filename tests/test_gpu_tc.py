@@ -238,3 +238,33 @@ def test_ragged_large_sizes_match_fp32_path():
         print(f"ragged n={s}: fp16 vs fp32 path rel err {err:.3e}")
         assert err < EMB_TOL["fp16"]
         assert float(e[i, :, s:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_embedder_from_adjacency_equals_embedder_from_features(prec):
+    """feeding the uint8 adjacency (input planes built on the device) gives the same embeddings
+    as the reference's fp32 (W, diag(deg)) features -- the planes are identical, so only the atomics' order in the
+    statistics can differ."""
+    gen = torch.Generator().manual_seed(11)
+    sizes = [150, 97, 64]
+    N = max(sizes)
+    sd = O.xavier_state_dict(2, 32, 3, 3, gen)
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=3,
+                    in_features=32, out_features=32, depth_of_mlp=3, constant_n_vertices=False)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    adj = torch.zeros((len(sizes), N, N), dtype=torch.uint8)
+    graphs = []
+    for g, n in enumerate(sizes):
+        W = torch.triu(torch.rand((n, n), generator=gen) < 0.2, 1)
+        W = W | W.T
+        adj[g, :n, :n] = W.to(torch.uint8)
+        graphs.append(O.adjacency_to_features(W.float()))
+    n_dev = torch.tensor(sizes, dtype=torch.int32, device=DEV)
+    with torch.no_grad():
+        ref = model.node_embedder.forward_fused(mt.from_list(graphs, dims=(1, 2)).to(DEV), prec).tensor.rename(None)
+        out = model.node_embedder.forward_fused_adjacency(adj.to(DEV), prec, n_dev)
+    assert rel_fro(out.cpu(), ref.cpu()) < 1e-3
+    for g, n in enumerate(sizes):
+        assert float(out[g, :, n:].abs().sum()) == 0
