@@ -119,3 +119,22 @@ def test_install_as_reference_aliases():
     import maskedtensor as top_mt       # noqa: E402
     from toolbox.losses import triplet_loss  # noqa: E402,F401
     assert ml.MlpBlock_Real is pkg.models.layers.MlpBlock_Real and top_mt.from_list is mt.from_list
+
+
+def test_device_side_input_construction_fails_loudly_off_gpu():
+    """No CPU fallback: the adjacency entry points reject CPU tensors / unsupported precisions with FgnnError."""
+    from graph_neural_net_b200._lib import FgnnError
+    from graph_neural_net_b200.loaders import data_generator as dg
+    adj = torch.zeros((2, 8, 8), dtype=torch.uint8)
+    with pytest.raises(FgnnError):
+        dg.adjacency_batch_to_tensor_representation(adj)
+    cfg = default_cfg()
+    model = pkg.models.get_siamese_model_exp(copy.deepcopy(cfg["arch"]), cfg["train"])
+    with pytest.raises(FgnnError):
+        model.node_embedder.forward_fused_adjacency(adj, "fp32")
+    with pytest.raises(FgnnError):
+        model.node_embedder.forward_fused_adjacency(adj, "bf16")
+    # the host-side reference construction is unchanged
+    W = torch.tensor([[0., 1., 1.], [1., 0., 0.], [1., 0., 0.]])
+    B = dg.adjacency_matrix_to_tensor_representation(W)
+    assert torch.equal(B[0], W) and torch.equal(B[1], torch.diag(torch.tensor([2., 1., 1.])))
