@@ -27,7 +27,7 @@ c_float_p = C.POINTER(C.c_float)
 class MlpParams(C.Structure):
     _fields_ = [("c_in", C.c_int32), ("c_out", C.c_int32), ("depth", C.c_int32),
                 ("w", C.c_void_p * FGNN_MAX_DEPTH), ("b", C.c_void_p * FGNN_MAX_DEPTH),
-                ("gn_w", C.c_void_p), ("gn_b", C.c_void_p), ("eps", C.c_float)]
+                ("gn_w", C.c_void_p), ("gn_b", C.c_void_p), ("eps", C.c_float), ("constant_n", C.c_int32)]
 
 
 class MlpGrads(C.Structure):
@@ -61,7 +61,7 @@ _SIGNATURES = {
     "fgnn_mlp_fwd_f32": (C.c_int, [C.POINTER(MlpParams), _vp, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fgnn_mlp_bwd_f32": (C.c_int, [C.POINTER(MlpParams), C.POINTER(MlpGrads), _vp, _vp, _vp, _vp, _i32, _i32,
                                    _vp, _vp, _sz, _vp]),
-    "fgnn_graphnorm_fwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, _i32, _i32, _i32, _vp, _vp]),
+    "fgnn_graphnorm_fwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, _i32, _i32, _i32, _i32, _vp, _vp]),
     "fgnn_matmul_fwd_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "fgnn_matmul_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "fgnn_features_from_adjacency_u8": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
@@ -72,6 +72,7 @@ _SIGNATURES = {
     "fgnn_ce_workspace_bytes": (_sz, [_i32, _i32]),
     "fgnn_ce_argmax_fwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fgnn_ce_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "fgnn_lap_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "fgnn_embed_workspace_bytes": (_sz, [C.POINTER(EmbedParams), _i32, _i32, _i32]),
     "fgnn_embed_fwd": (C.c_int, [C.POINTER(EmbedParams), _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "fgnn_embed_fwd_adjacency_u8": (C.c_int, [C.POINTER(EmbedParams), _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),

@@ -13,13 +13,32 @@ import torch
 from . import _lib as L
 
 
-def _npg(n_dev: Optional[torch.Tensor]):
-    return L.ptr(n_dev) if n_dev is not None else None
+def _npg(n_dev: Optional[torch.Tensor], G: Optional[int] = None):
+    """Device pointer of the int32 per-graph vertex counts (or NULL).  The kernels index other planes with these
+    values, so the tensor is checked here: CUDA, int32, contiguous, one entry per graph."""
+    if n_dev is None:
+        return None
+    if not isinstance(n_dev, torch.Tensor) or not n_dev.is_cuda:
+        raise L.FgnnError("sizes must be a CUDA tensor (there is no CPU fallback)")
+    if n_dev.dtype != torch.int32 or n_dev.dim() != 1 or not n_dev.is_contiguous():
+        raise L.FgnnError(f"sizes must be a contiguous 1-D int32 tensor, got {n_dev.dtype} {tuple(n_dev.shape)}")
+    if G is not None and n_dev.numel() != G:
+        raise L.FgnnError(f"sizes has {n_dev.numel()} entries for a batch of {G} graphs")
+    return L.ptr(n_dev)
+
+
+def check_user_sizes(n_dev: torch.Tensor, G: int, N: int) -> torch.Tensor:
+    """Validate caller-supplied vertex counts (one host round trip): 1 <= n_g <= N for every graph."""
+    _npg(n_dev, G)
+    lo, hi = int(n_dev.min()), int(n_dev.max())
+    if lo < 1 or hi > N:
+        raise L.FgnnError(f"sizes must satisfy 1 <= n <= {N}; got range [{lo}, {hi}]")
+    return n_dev
 
 
 def make_mlp_params(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
                     gn_w: Optional[torch.Tensor], gn_b: Optional[torch.Tensor], eps: float,
-                    keep: list) -> L.MlpParams:
+                    keep: list, constant_n: bool = True) -> L.MlpParams:
     """Fill an fgnn_mlp_params from Conv2d/GraphNorm tensors.  `keep` receives every temporary
     that must outlive the C call (contiguous copies)."""
     p = L.MlpParams()
@@ -49,6 +68,7 @@ def make_mlp_params(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tens
         p.gn_w = None
         p.gn_b = None
     p.eps = float(eps)
+    p.constant_n = 1 if constant_n else 0
     return p
 
 
@@ -56,12 +76,12 @@ class MlpFunction(torch.autograd.Function):
     """MlpBlock_Real forward/backward (reference models/layers.py:109-131)."""
 
     @staticmethod
-    def forward(ctx, x, n_dev, eps, depth, gn_w, gn_b, *wb):
+    def forward(ctx, x, n_dev, eps, depth, constant_n, gn_w, gn_b, *wb):
         lib = L.get_lib()
         x = L.require_cuda_f32(x, "x")
         weights, biases = wb[:depth], wb[depth:]
         keep = []
-        p = make_mlp_params(weights, biases, gn_w, gn_b, eps, keep)
+        p = make_mlp_params(weights, biases, gn_w, gn_b, eps, keep, constant_n)
         G, Ci, N, N2 = x.shape
         if N != N2 or Ci != p.c_in:
             raise L.FgnnError(f"MlpBlock_Real: bad input shape {tuple(x.shape)} for c_in={p.c_in}")
@@ -73,7 +93,7 @@ class MlpFunction(torch.autograd.Function):
                                      L.ptr(ws), ws.numel(), L.stream_ptr(x.device)), "fgnn_mlp_fwd_f32")
         ctx.save_for_backward(x, stats, n_dev if n_dev is not None else torch.empty(0), gn_w, gn_b, *wb)
         ctx.has_n = n_dev is not None
-        ctx.eps, ctx.depth = eps, depth
+        ctx.eps, ctx.depth, ctx.constant_n = eps, depth, constant_n
         return y
 
     @staticmethod
@@ -84,7 +104,7 @@ class MlpFunction(torch.autograd.Function):
         depth = ctx.depth
         weights, biases = wb[:depth], wb[depth:]
         keep = []
-        p = make_mlp_params(weights, biases, gn_w, gn_b, ctx.eps, keep)
+        p = make_mlp_params(weights, biases, gn_w, gn_b, ctx.eps, keep, ctx.constant_n)
         g = L.MlpGrads()
         dws = [torch.zeros_like(w, dtype=torch.float32).reshape(w.shape[0], -1).contiguous() for w in weights]
         dbs = [torch.zeros(w.shape[0], device=x.device, dtype=torch.float32) for w in weights]
@@ -104,7 +124,7 @@ class MlpFunction(torch.autograd.Function):
                 "fgnn_mlp_bwd_f32")
         grads_w = [dws[k].reshape(weights[k].shape) for k in range(depth)]
         grads_b = [dbs[k] if biases[k] is not None else None for k in range(depth)]
-        return (dx, None, None, None,
+        return (dx, None, None, None, None,
                 dgw.reshape(gn_w.shape) if gn_w is not None else None,
                 dgb.reshape(gn_b.shape) if gn_b is not None else None, *grads_w, *grads_b)
 
@@ -240,7 +260,7 @@ class CrossEntropyIdentityFunction(torch.autograd.Function):
         return ds, None
 
 
-def graphnorm_fwd(x: torch.Tensor, n_dev, gn_w, gn_b, eps: float) -> torch.Tensor:
+def graphnorm_fwd(x: torch.Tensor, n_dev, gn_w, gn_b, eps: float, constant_n: bool = True) -> torch.Tensor:
     """GraphNorm / normalize forward (reference models/layers.py:68-80); no autograd (use MlpBlock_Real
     for training -- the standalone norm is not on the training path)."""
     lib = L.get_lib()
@@ -253,7 +273,8 @@ def graphnorm_fwd(x: torch.Tensor, n_dev, gn_w, gn_b, eps: float) -> torch.Tenso
     gw = L.require_cuda_f32(gn_w.detach().reshape(-1), "weight") if gn_w is not None else None
     gb = L.require_cuda_f32(gn_b.detach().reshape(-1), "bias") if gn_b is not None else None
     L.check(lib.fgnn_graphnorm_fwd_f32(L.ptr(x), L.ptr(y), L.ptr(stats), L.ptr(gw), L.ptr(gb), float(eps),
-                                       G, Cc, N, _npg(n_dev), L.stream_ptr(x.device)), "fgnn_graphnorm_fwd_f32")
+                                       1 if constant_n else 0, G, Cc, N, _npg(n_dev, G), L.stream_ptr(x.device)),
+            "fgnn_graphnorm_fwd_f32")
     return y
 
 

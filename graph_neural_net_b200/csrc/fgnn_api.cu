@@ -177,9 +177,9 @@ int fgnn_mlp_bwd_f32(const fgnn_mlp_params* p, const fgnn_mlp_grads* g, const fl
 }
 
 int fgnn_graphnorm_fwd_f32(const float* x, float* y, float* stats, const float* gn_w,
-                           const float* gn_b, float eps, int32_t G, int32_t C, int32_t N,
+                           const float* gn_b, float eps, int32_t constant_n, int32_t G, int32_t C, int32_t N,
                            const int32_t* n_per_graph, void* stream) {
-  return f32::graphnorm_fwd(x, y, stats, gn_w, gn_b, eps, G, C, N, n_per_graph, (cudaStream_t)stream);
+  return f32::graphnorm_fwd(x, y, stats, gn_w, gn_b, eps, constant_n, G, C, N, n_per_graph, (cudaStream_t)stream);
 }
 
 int fgnn_matmul_fwd_f32(const float* a, const float* b, float* out, int32_t G, int32_t C, int32_t N,
@@ -195,6 +195,11 @@ int fgnn_matmul_bwd_f32(const float* a, const float* b, const float* dout, float
   if (db)  // db = a^T @ dout
     if (int e = f32::matmul_fwd(a, dout, db, G, C, N, n_per_graph, st, true, false)) return e;
   return FGNN_OK;
+}
+
+int fgnn_lap_fwd(const float* scores, int32_t* col_of_row, int32_t* correct, double* total_cost, int32_t G,
+                 int32_t N, const int32_t* n_per_graph, void* stream) {
+  return lap::lap_fwd(scores, col_of_row, correct, total_cost, G, N, n_per_graph, (cudaStream_t)stream);
 }
 
 int fgnn_features_from_adjacency_u8(const uint8_t* adj, float* out, int32_t G, int32_t N, const int32_t* n_per_graph,

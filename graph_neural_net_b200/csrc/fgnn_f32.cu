@@ -115,7 +115,7 @@ conv_chain_fwd_kernel(ChainArgs a, const float* __restrict__ x, float* __restric
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 plane_stats_kernel(const float* __restrict__ z, float* __restrict__ stats, int C, int N,
-                   const int32_t* __restrict__ n_per_graph, float eps) {
+                   const int32_t* __restrict__ n_per_graph, float eps, int constant_n) {
   const int gc = blockIdx.x;
   const int g = gc / C;
   const int n = graph_n(n_per_graph, g, N);
@@ -144,7 +144,7 @@ plane_stats_kernel(const float* __restrict__ z, float* __restrict__ stats, int C
     double var = sh[1][0] / cnt - mean * mean;
     if (var < 0) var = 0;
     stats[2 * gc] = (float)mean;
-    stats[2 * gc + 1] = (float)(1.0 / (2.0 * sqrt((double)n * (var + (double)eps))));
+    stats[2 * gc + 1] = (float)(1.0 / (2.0 * sqrt((double)(constant_n ? N : n) * (var + (double)eps))));
   }
 }
 
@@ -453,11 +453,10 @@ int run_conv1x1(const float* w, const float* b, int c_in, int c_out, bool transp
   a.wt[0] = wt_scratch;
   a.b[0] = b;
   const size_t smem = (size_t)2 * a.cop * kPixThreads * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  // set on every call: the attribute is per device and the call is cheap (a process may drive several GPUs)
+  {
     FGNN_CUDA(cudaFuncSetAttribute(conv_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    2 * kMaxC * kPixThreads * (int)sizeof(float)));
-    attr_set = true;
   }
   FGNN_CHECK_ARG(c_out <= kMaxC, "conv1x1: c_out %d unsupported (max %d)", c_out, kMaxC);
   long P = (long)N * N;
@@ -510,10 +509,10 @@ static int prepare_chain(const fgnn_mlp_params& p, ChainArgs& a, Arena& ar, cuda
 }
 
 int graphnorm_fwd(const float* x, float* y, float* stats, const float* gw, const float* gb, float eps,
-                  int G, int C, int N, const int32_t* n_per_graph, cudaStream_t st) {
+                  int constant_n, int G, int C, int N, const int32_t* n_per_graph, cudaStream_t st) {
   if (int e = check_dims(G, C, N)) return e;
   FGNN_CHECK_ARG(x && y && stats, "null pointer");
-  plane_stats_kernel<<<G * C, 256, 0, st>>>(x, stats, C, N, n_per_graph, eps);
+  plane_stats_kernel<<<G * C, 256, 0, st>>>(x, stats, C, N, n_per_graph, eps, constant_n);
   FGNN_LAUNCHED();
   long P = (long)N * N;
   dim3 grid((unsigned)min((long)64, (P + 255) / 256), G * C);
@@ -530,17 +529,16 @@ int mlp_fwd(const fgnn_mlp_params& p, const float* x, float* y, float* stats, in
   ChainArgs a;
   if (int e = prepare_chain(p, a, ar, st)) return e;
   const size_t smem = (size_t)2 * a.cop * kPixThreads * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  // set on every call: the attribute is per device and the call is cheap (a process may drive several GPUs)
+  {
     FGNN_CUDA(cudaFuncSetAttribute(conv_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    2 * kMaxC * kPixThreads * (int)sizeof(float)));
-    attr_set = true;
   }
   long P = (long)N * N;
   dim3 grid((unsigned)((P + kPixThreads - 1) / kPixThreads), G);
   conv_chain_fwd_kernel<<<grid, kPixThreads, smem, st>>>(a, x, y, N, n_per_graph);
   FGNN_LAUNCHED();
-  return graphnorm_fwd(y, y, stats, p.gn_w, p.gn_b, p.eps, G, p.c_out, N, n_per_graph, st);
+  return graphnorm_fwd(y, y, stats, p.gn_w, p.gn_b, p.eps, p.constant_n, G, p.c_out, N, n_per_graph, st);
 }
 
 int matmul_fwd(const float* a, const float* b, float* out, int G, int C, int N,

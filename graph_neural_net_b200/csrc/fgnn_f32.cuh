@@ -19,7 +19,7 @@ int mlp_bwd(const fgnn_mlp_params& p, const fgnn_mlp_grads& g, const float* x, c
             const float* dy, float* dx, int G, int N, const int32_t* n_per_graph, void* ws,
             size_t ws_bytes, cudaStream_t st);
 int graphnorm_fwd(const float* x, float* y, float* stats, const float* gw, const float* gb, float eps,
-                  int G, int C, int N, const int32_t* n_per_graph, cudaStream_t st);
+                  int constant_n, int G, int C, int N, const int32_t* n_per_graph, cudaStream_t st);
 int matmul_fwd(const float* a, const float* b, float* out, int G, int C, int N,
                const int32_t* n_per_graph, cudaStream_t st, bool trans_a = false, bool trans_b = false);
 int colmax_fwd(const float* x, float* out, int32_t* argmax, int G, int C, int N,

@@ -59,7 +59,7 @@ gn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ z, c
 __global__ void gn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                     const float* __restrict__ stats, const float* __restrict__ sums,
                                     const float* __restrict__ gw, float* __restrict__ dz, int C, int N,
-                                    const int32_t* __restrict__ n_per_graph) {
+                                    const int32_t* __restrict__ n_per_graph, int constant_n) {
   const int gc = blockIdx.y;
   const int g = gc / C, c = gc % C;
   const int n = graph_n(n_per_graph, g, N);
@@ -67,7 +67,7 @@ __global__ void gn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
   const float mu = stats[2 * gc], inv = stats[2 * gc + 1];
   const float cnt = (float)n * (float)n;
   const float m1 = sums[2 * gc] / cnt;
-  const float m2 = sums[2 * gc + 1] / cnt * 4.f * (float)n * inv * inv;   // mean(g (z-mu)) / (var + eps)
+  const float m2 = sums[2 * gc + 1] / cnt * 4.f * (float)(constant_n ? N : n) * inv * inv;   // mean(g (z-mu)) / (var + eps)
   const float w = (gw ? gw[c] : 1.f) * inv;
   for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long)gridDim.x * blockDim.x) {
     int i = (int)(p / N), j = (int)(p % N);
@@ -165,7 +165,7 @@ int mlp_bwd(const fgnn_mlp_params& p, const fgnn_mlp_grads& gr, const float* x, 
     FGNN_LAUNCHED();
     {
       dim3 grid((unsigned)std::min<long>(64, (P + 255) / 256), gc * Co);
-      gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dyc, h[depth - 1], stc, smc, p.gn_w, dcur, Co, N, n_c);
+      gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dyc, h[depth - 1], stc, smc, p.gn_w, dcur, Co, N, n_c, p.constant_n);
       FGNN_LAUNCHED();
     }
     // 3. layers in reverse

@@ -252,6 +252,7 @@ struct CoefArgs {
   const float* gw[2];
   const float* gb[2];
   float eps[2];
+  int constant_n[2];
   int nmlp, C, N;
   const int32_t* n_per_graph;
 };
@@ -267,7 +268,7 @@ __global__ void finalize_coef_kernel(CoefArgs a, int total) {
   const double mean = S / cnt;
   double var = SS / cnt - mean * mean;
   if (var < 0) var = 0;
-  const double sc = (double)(a.gw[m] ? a.gw[m][c] : 1.f) / (2.0 * sqrt((double)n * (var + (double)a.eps[m])));
+  const double sc = (double)(a.gw[m] ? a.gw[m][c] : 1.f) / (2.0 * sqrt((double)(a.constant_n[m] ? a.N : n) * (var + (double)a.eps[m])));
   a.coef[m][((long)g * a.C + c) * 2] = (float)sc;
   a.coef[m][((long)g * a.C + c) * 2 + 1] = (float)((double)(a.gb[m] ? a.gb[m][c] : 0.f) - sc * mean);
 }
@@ -1221,14 +1222,15 @@ int make_map3(CUtensorMap* m, int fmt_is_bf16, const void* base, uint64_t d0, ui
   return FGNN_OK;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+int num_sms() {   // of the CURRENT device (a process may drive several GPUs): not cached across devices
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
 }
 
@@ -1255,12 +1257,9 @@ int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const f
   const int grid = num_sms();
 #define FGNN_MM_LAUNCH(BNV)                                                                              \
   do {                                                                                                   \
-    static bool attr = false;                                                                            \
-    if (!attr) {                                                                                         \
-      FGNN_CUDA(cudaFuncSetAttribute(tc_matmul_kernel<T, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)MatmulCfg<BNV>::kSmemBytes));                                  \
-      attr = true;                                                                                       \
-    }                                                                                                    \
+    /* per device and cheap: set on every call */                                                        \
+    FGNN_CUDA(cudaFuncSetAttribute(tc_matmul_kernel<T, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)MatmulCfg<BNV>::kSmemBytes));                                    \
     tc_matmul_kernel<T, BNV><<<grid, 192, MatmulCfg<BNV>::kSmemBytes, st>>>(ma, mb, mo32, mo31, a);                   \
   } while (0)
   prof::begin(prof::kMatmul, st);
@@ -1338,15 +1337,13 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   FGNN_CHECK_ARG(smem <= 227 * 1024, "MLP kernel needs %zu bytes of shared memory", smem);
   const bool pool = a.rowenc[0] != nullptr;
   FGNN_CHECK_ARG(!pool || NMLP == 1, "fused pooling is only built for single-MLP launches");
-  static size_t attr_bytes[2] = {0, 0};
-  if (smem > attr_bytes[pool]) {
+  {   // the opt-in is per device and cheap: set on every call
     if (pool) {
       if constexpr (NMLP == 1)
         FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
       FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    attr_bytes[pool] = smem;
   }
   FGNN_CUDA(cudaMemsetAsync(L.stat_acc, 0, (size_t)G * NMLP * COUT * 2 * sizeof(double), st));
   long total_tiles = (long)G * ((geo.PSC + kTileM - 1) / kTileM);
@@ -1439,6 +1436,7 @@ int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int3
     ca.gw[m] = M.mp[m]->gn_w;
     ca.gb[m] = M.mp[m]->gn_b;
     ca.eps[m] = M.mp[m]->eps;
+    ca.constant_n[m] = M.mp[m]->constant_n;
   }
   const int total = G * M.nmlp * C;
   prof::begin(prof::kStats, st);

@@ -24,4 +24,9 @@ int debug_mlp(int precision, const fgnn_mlp_params& mp, const float* x, float* y
 void dump_timing();
 
 }  // namespace tc
+
+namespace lap {
+int lap_fwd(const float* scores, int32_t* col_of_row, int32_t* correct, double* total_cost, int G, int N,
+            const int32_t* n_per_graph, cudaStream_t st);
+}  // namespace lap
 }  // namespace fgnn

@@ -80,6 +80,7 @@ class MaskedTensor:
         self.dtype = self.tensor.dtype
         self.device = self.tensor.device
         self._sizes_cache = None
+        self._sizes_dev = None        # int32 device copy of the sizes, uploaded once per batch
         if adjust_mask:
             self._adjust_mask_()
         if apply_mask:
@@ -122,8 +123,17 @@ class MaskedTensor:
         return self._sizes_cache
 
     def sizes_i32(self, device=None) -> torch.Tensor:
-        dev = self.device if device is None else device
-        return torch.tensor(self.sizes_host(), dtype=torch.int32, device=dev)
+        dev = torch.device(self.device if device is None else device)
+        if self._sizes_dev is None or self._sizes_dev.device != dev:
+            self._sizes_dev = torch.tensor(self.sizes_host(), dtype=torch.int32, device=dev)
+        return self._sizes_dev
+
+    def _inherit_sizes(self, other: "MaskedTensor") -> "MaskedTensor":
+        """Operator outputs keep the masks of their input: reuse its validated sizes (no re-validation, no
+        device synchronisation, no second upload)."""
+        self._sizes_cache = other._sizes_cache
+        self._sizes_dev = other._sizes_dev
+        return self
 
     # ---- torch function protocol ---------------------------------------------------------
     @classmethod

@@ -29,7 +29,7 @@ def _unwrap(x):
 
         def rewrap(t, out_names=names):
             keep = {k: v for k, v in masks.items() if k in out_names}
-            return MaskedTensor(t.rename(*out_names), keep, adjust_mask=False, apply_mask=False)
+            return MaskedTensor(t.rename(*out_names), keep, adjust_mask=False, apply_mask=False)._inherit_sizes(x)
         return plain, n_dev, rewrap
     return x, None, (lambda t, out_names=None: t)
 
@@ -40,7 +40,7 @@ def normalize(b, constant_n_vertices=True, eps=1e-05):
     plain, n_dev, rewrap = _unwrap(b)
     if not constant_n_vertices and n_dev is None:
         raise TypeError("constant_n_vertices=False needs a MaskedTensor input")
-    return rewrap(_ops.graphnorm_fwd(plain, n_dev, None, None, eps))
+    return rewrap(_ops.graphnorm_fwd(plain, n_dev, None, None, eps, constant_n_vertices))
 
 
 class GraphNorm(nn.Module):
@@ -65,7 +65,7 @@ class GraphNorm(nn.Module):
 
     def forward(self, b):
         plain, n_dev, rewrap = _unwrap(b)
-        return rewrap(_ops.graphnorm_fwd(plain, n_dev, self.weight, self.bias, self.eps))
+        return rewrap(_ops.graphnorm_fwd(plain, n_dev, self.weight, self.bias, self.eps, self.constant_n_vertices))
 
 
 def _init_weights(layer):
@@ -102,7 +102,8 @@ class MlpBlock_Real(nn.Module):
         plain, n_dev, rewrap = _unwrap(inputs)
         ws = [c.weight for c in self.convs]
         bs = [c.bias for c in self.convs]
-        y = _ops.MlpFunction.apply(plain, n_dev, self.gn.eps, len(ws), self.gn.weight, self.gn.bias, *ws, *bs)
+        y = _ops.MlpFunction.apply(plain, n_dev, self.gn.eps, len(ws), bool(self.cst_vertices), self.gn.weight,
+                                   self.gn.bias, *ws, *bs)
         return rewrap(y)
 
 

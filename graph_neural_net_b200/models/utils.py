@@ -148,7 +148,7 @@ class Network(nn.Module):
         for i, trio in enumerate(blocks):
             for name, mlp in zip(('mlp1', 'mlp2', 'mlp3'), trio):
                 mp = _ops.make_mlp_params([c.weight for c in mlp.convs], [c.bias for c in mlp.convs],
-                                          mlp.gn.weight, mlp.gn.bias, mlp.gn.eps, keep)
+                                          mlp.gn.weight, mlp.gn.bias, mlp.gn.eps, keep, bool(mlp.cst_vertices))
                 setattr(p.block[i], name, mp)
         return p
 

@@ -1,8 +1,8 @@
 """Alignment accuracy metrics (reference toolbox/metrics.py:92-141).
 
 accuracy_max is computed on the device in the same pass as the loss (row argmax == row index);
-accuracy_linear_assignment stays on the host like the reference (scipy Hungarian per graph) -- it is
-a 'next' row of the scope table, not part of the CUDA hot path.
+accuracy_linear_assignment (the metric training_step actually calls, trainers.py:53,74) runs a batched
+shortest-augmenting-path solver on the device (csrc/fgnn_lap.cu) instead of one host scipy call per graph.
 """
 import numpy as np
 import torch
@@ -25,19 +25,38 @@ def accuracy_max(weights, labels=None, aggregate_score=True):
     return [c / s for c, s in zip(correct, sizes)]
 
 
+def linear_assignment(rawscores):
+    """Optimal matchings of a batch on the device (fgnn_lap_fwd): -> (col_of_row (B,N) int32 with -1 in padded rows,
+    correct (B,) int32, total_cost (B,) float64).  One CTA per graph runs the shortest-augmenting-path algorithm scipy
+    uses, in double precision, on cost = -scores."""
+    import ctypes as C
+    from .. import _lib as L
+    scores, n_dev, _ = _as_batch(rawscores)
+    scores = L.require_cuda_f32(scores.detach(), "rawscores")
+    G, N, M = scores.shape
+    if N != M:
+        raise L.FgnnError("rawscores must be (B,N,N)")
+    cols = torch.empty((G, N), dtype=torch.int32, device=scores.device)
+    correct = torch.empty(G, dtype=torch.int32, device=scores.device)
+    cost = torch.empty(G, dtype=torch.float64, device=scores.device)
+    L.check(L.get_lib().fgnn_lap_fwd(L.ptr(scores), L.ptr(cols), L.ptr(correct), L.ptr(cost), G, N,
+                                     _ops._npg(n_dev, G), L.stream_ptr(scores.device)), "fgnn_lap_fwd")
+    return cols, correct, cost
+
+
 def accuracy_linear_assignment(rawscores, labels=None, aggregate_score=True):
-    """Hungarian matching accuracy.  log_softmax is a per-row shift, which does not change the optimal
-    assignment, so the raw scores go straight to scipy after ONE device-to-host copy of the batch."""
-    from scipy.optimize import linear_sum_assignment
+    """Hungarian matching accuracy (reference toolbox/metrics.py:92-116) computed on the device: log_softmax is a
+    per-row shift, which does not change the optimal assignment, so the raw scores are matched directly; only
+    the per-graph hit counts (B int32) travel to the host.  `labels` (a list of per-graph index arrays) compares
+    the device matching with them on the host, as the reference does."""
     scores, n_dev, sizes = _as_batch(rawscores)
-    host = scores.detach().cpu().numpy()
+    cols, correct, _ = linear_assignment(rawscores)
     sizes = sizes.cpu().numpy().astype(np.int64)
-    acc, total, per = 0, 0, []
-    for i, n in enumerate(sizes):
-        label = labels[i] if labels else np.arange(n)
-        _, preds = linear_sum_assignment(-host[i, :n, :n].astype(np.float64))
-        hit = int(np.sum(preds == label))
-        acc += hit
-        total += int(n)
-        per.append(hit / n)
-    return (acc, total) if aggregate_score else per
+    if labels:
+        cols_h = cols.cpu().numpy()
+        hits = np.array([int(np.sum(cols_h[i, :n] == np.asarray(labels[i])[:n])) for i, n in enumerate(sizes)])
+    else:
+        hits = correct.cpu().numpy().astype(np.int64)
+    if aggregate_score:
+        return int(hits.sum()), int(sizes.sum())
+    return [h / n for h, n in zip(hits, sizes)]

@@ -58,6 +58,10 @@ typedef struct {
   const float* gn_w;
   const float* gn_b;
   float eps; /* 1e-5 in the reference */
+  /* GraphNorm's n (models/layers.py:76-79): 1 = constant_n_vertices=True, n = the padded size N even for a ragged
+   * batch (the reference's default; mean / variance still run over each graph's own n_g x n_g block);
+   * 0 = constant_n_vertices=False, n = the graph's own vertex count n_g.  Irrelevant when n_per_graph is NULL. */
+  int32_t constant_n;
 } fgnn_mlp_params;
 
 /* Gradients of the above, same shapes; accumulated into (+=), caller zeroes them. */
@@ -103,9 +107,9 @@ int fgnn_mlp_bwd_f32(const fgnn_mlp_params* p, const fgnn_mlp_grads* g, const fl
                      void* stream);
 
 /* GraphNorm.forward / normalize (models/layers.py:68-80).  gn_w/gn_b may be NULL (plain
- * normalize).  stats as above (may be NULL). */
+ * normalize).  stats as above (may be NULL).  constant_n: see fgnn_mlp_params. */
 int fgnn_graphnorm_fwd_f32(const float* x, float* y, float* stats, const float* gn_w,
-                           const float* gn_b, float eps, int32_t G, int32_t C, int32_t N,
+                           const float* gn_b, float eps, int32_t constant_n, int32_t G, int32_t C, int32_t N,
                            const int32_t* n_per_graph, void* stream);
 
 /* Matmul.forward: torch.matmul over the last two dims (models/layers.py:161-162).
@@ -151,6 +155,15 @@ int fgnn_ce_argmax_fwd_f32(const float* scores, float* ce_sum, int32_t* correct,
  * reduction and the upstream gradient. */
 int fgnn_ce_bwd_f32(const float* scores, const float* row_lse, const float* coef, float* dscores,
                     int32_t G, int32_t N, const int32_t* n_per_graph, void* stream);
+
+/* accuracy_linear_assignment (toolbox/metrics.py:92-116), the metric training_step / validation_step call
+ * (models/trainers.py:53,74): per graph the assignment col(i) maximising sum_i scores[i, col(i)] -- identical to
+ * scipy.optimize.linear_sum_assignment on -log_softmax(scores), since log_softmax only shifts rows -- found on the
+ * device by shortest augmenting paths in double precision, one CTA per graph.  scores (G,N,N);
+ * col_of_row (G,N) int32 (rows >= n_g get -1; may be NULL); correct[G] = #rows with col(i) == i;
+ * total_cost[G] = sum_i -scores[i, col(i)] (may be NULL). */
+int fgnn_lap_fwd(const float* scores, int32_t* col_of_row, int32_t* correct, double* total_cost, int32_t G,
+                 int32_t N, const int32_t* n_per_graph, void* stream);
 
 /* ---- fused embedder (the hot path proper) ------------------------------------------------ */
 

@@ -175,6 +175,30 @@ def accuracy_max(score_list: Sequence[Tensor]) -> Tuple[int, int]:
 
 
 # --------------------------------------------------------------------------- #
+# accuracy_linear_assignment                    toolbox/metrics.py:92-116
+# --------------------------------------------------------------------------- #
+def linear_assignment_preds(scores: Tensor):
+    """Hungarian matching maximising sum_i log_softmax(scores)[i, pred_i] (scipy, as the reference:
+    toolbox/metrics.py:100-106).  Returns the column assigned to each row."""
+    from scipy.optimize import linear_sum_assignment
+    cost = -torch.log_softmax(scores, -1).detach().cpu().numpy()
+    return linear_sum_assignment(cost)[1]
+
+
+def accuracy_linear_assignment(score_list: Sequence[Tensor]) -> Tuple[int, int]:
+    """(#rows matched to their own index by the optimal assignment, #rows).  toolbox/metrics.py:92-116
+    (labels=None, aggregate_score=True)."""
+    import numpy as np
+    correct = 0
+    total = 0
+    for s in score_list:
+        preds = linear_assignment_preds(s)
+        correct += int(np.sum(preds == np.arange(s.shape[0])))
+        total += s.shape[0]
+    return correct, total
+
+
+# --------------------------------------------------------------------------- #
 # Input construction                            loaders/data_generator.py:118-125
 # --------------------------------------------------------------------------- #
 def adjacency_to_features(W: Tensor) -> Tensor:

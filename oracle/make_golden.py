@@ -28,7 +28,7 @@ from models.layers import MlpBlock_Real, GraphNorm, normalize, Matmul, ColumnMax
 from loaders import data_generator as dg  # noqa: E402
 from maskedtensors import maskedtensor as mt  # noqa: E402
 from toolbox.losses import triplet_loss  # noqa: E402
-from toolbox.metrics import accuracy_max  # noqa: E402
+from toolbox.metrics import accuracy_max, accuracy_linear_assignment  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 SEED = 3787
@@ -208,9 +208,149 @@ def layers_case(name):
     print(name, "ok")
 
 
+def headline_case(name, generative, n, p, noise, pairs, c, num_blocks, depth, perturb, with_grads):
+    """Benched shapes (BASELINE.json configs[1] / configs[2]): embeddings, scores, loss, both accuracies, and
+    optionally every parameter gradient.  Adjacencies are stored bit-packed; `perturb=False` keeps the reference's
+    own init (xavier weights, zero biases, unit GraphNorm affine) -- what bench.py runs."""
+    seed_all(SEED)
+    model = build_model(c, num_blocks, depth)
+    if perturb:
+        perturb_(model, torch.Generator().manual_seed(SEED + 1))
+    W1, W2 = gen_pairs(generative, n, p, noise, pairs)
+    x1 = torch.stack([dg.adjacency_matrix_to_tensor_representation(w) for w in W1])
+    x2 = torch.stack([dg.adjacency_matrix_to_tensor_representation(w) for w in W2])
+    model.train()
+    with torch.set_grad_enabled(with_grads):
+        e1 = model.node_embedder({"input": x1})["ne/suffix"]
+        e2 = model.node_embedder({"input": x2})["ne/suffix"]
+        scores = torch.matmul(torch.transpose(e1, 1, 2), e2)          # models/trainers.py:67
+        loss_mean = triplet_loss("mean")(scores)
+    correct, total = accuracy_max(scores)
+    lap_correct, lap_total = accuracy_linear_assignment(scores)
+    arrs = dict(sd_np(model))
+    arrs.update(
+        W1_bits=np.packbits(torch.stack(W1).numpy().astype(np.uint8), axis=-1),
+        W2_bits=np.packbits(torch.stack(W2).numpy().astype(np.uint8), axis=-1),
+        emb1=e1.detach().numpy(), emb2=e2.detach().numpy(), scores=scores.detach().numpy(),
+        loss_mean=np.float64(loss_mean.item()), acc=np.array([correct, total], dtype=np.int64),
+        acc_lap=np.array([lap_correct, lap_total], dtype=np.int64),
+        meta=np.array([n, c, num_blocks, depth, pairs], dtype=np.int64))
+    if with_grads:
+        model.zero_grad()
+        loss_mean.backward()
+        for k, p_ in model.named_parameters():
+            arrs["grad/" + k] = p_.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(name, "loss", float(loss_mean), "acc", correct, total, "lap", lap_correct, lap_total)
+
+
+def trained_case(name, n, p, noise, c, num_blocks, depth, steps, batch, eval_pairs):
+    """A briefly TRAINED default-architecture model (the reference's own training_step arithmetic: Adam lr 1e-3 on
+    triplet_loss('mean'), models/trainers.py:70-76,92-104), so that row-argmax and LAP matchings have real margins:
+    parity of predictions is only meaningful on such weights."""
+    seed_all(SEED)
+    model = build_model(c, num_blocks, depth)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    crit = triplet_loss("mean")
+    for it in range(steps):
+        W1, W2 = gen_pairs("ErdosRenyi", n, p, noise, batch)
+        x1 = torch.stack([dg.adjacency_matrix_to_tensor_representation(w) for w in W1])
+        x2 = torch.stack([dg.adjacency_matrix_to_tensor_representation(w) for w in W2])
+        opt.zero_grad()
+        loss = crit(model({"input": x1}, {"input": x2}))
+        loss.backward()
+        opt.step()
+        if it % 20 == 0 or it == steps - 1:
+            print(name, "step", it, "loss", float(loss), flush=True)
+    W1, W2 = gen_pairs("ErdosRenyi", n, p, noise, eval_pairs)
+    x1 = torch.stack([dg.adjacency_matrix_to_tensor_representation(w) for w in W1])
+    x2 = torch.stack([dg.adjacency_matrix_to_tensor_representation(w) for w in W2])
+    with torch.no_grad():
+        scores = model({"input": x1}, {"input": x2})
+        e1 = model.node_embedder({"input": x1})["ne/suffix"]
+    correct, total = accuracy_max(scores)
+    lap_correct, lap_total = accuracy_linear_assignment(scores)
+    from scipy.optimize import linear_sum_assignment
+    lsm = torch.log_softmax(scores, -1).numpy()
+    lap_preds = np.stack([linear_sum_assignment(-w)[1] for w in lsm])
+    arrs = dict(sd_np(model))
+    arrs.update(W1=torch.stack(W1).numpy().astype(np.uint8), W2=torch.stack(W2).numpy().astype(np.uint8),
+                emb1=e1.numpy(), scores=scores.numpy(), loss_mean=np.float64(crit(scores).item()),
+                acc=np.array([correct, total], dtype=np.int64), acc_lap=np.array([lap_correct, lap_total], dtype=np.int64),
+                argmax=scores.argmax(-1).numpy().astype(np.int32), lap_preds=lap_preds.astype(np.int32),
+                meta=np.array([n, c, num_blocks, depth, eval_pairs], dtype=np.int64))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(name, "acc_max", correct, total, "acc_lap", lap_correct, lap_total)
+
+
+def ragged_cstn_case(name, sizes, p, noise, c, num_blocks, depth):
+    """The reference's DEFAULT on a ragged batch: constant_n_vertices=True modules fed MaskedTensors (commander_explore
+    builds the model without the flag, collate_fn_pair feeds MaskedTensors): statistics run over each graph's own
+    block but GraphNorm's n is the padded size (models/layers.py:76-77).  Also the ragged GRADIENT fixture:
+    loss = sum_b CE_b / sum_b n_b over the per-graph dense loop (constant_n_vertices=False semantics)."""
+    seed_all(SEED)
+    model = build_model(c, num_blocks, depth, cst=True)
+    perturb_(model, torch.Generator().manual_seed(SEED + 4))
+    g1, g2, W1, W2 = [], [], [], []
+    for n in sizes:
+        g, W = dg.GENERATOR_FUNCTIONS["ErdosRenyi"](p, n)
+        Wn = dg.noise_erdos_renyi(g, W, noise, p)
+        W1.append(W), W2.append(Wn)
+        g1.append(dg.adjacency_matrix_to_tensor_representation(W))
+        g2.append(dg.adjacency_matrix_to_tensor_representation(Wn))
+    m1 = mt.from_list(g1, dims=(1, 2), base_name="N")
+    with torch.no_grad():
+        me1 = model.node_embedder({"input": m1})["ne/suffix"]
+    # gradients of the ragged loss through the per-graph loop
+    model.zero_grad()
+    per1 = [model.node_embedder({"input": g.unsqueeze(0)})["ne/suffix"][0] for g in g1]
+    per2 = [model.node_embedder({"input": g.unsqueeze(0)})["ne/suffix"][0] for g in g2]
+    per_scores = [torch.matmul(a.t(), b) for a, b in zip(per1, per2)]
+    loss = triplet_loss("mean")(mt.from_list(per_scores, dims=(0, 1)))
+    loss.backward()
+    arrs = dict(sd_np(model))
+    arrs.update(sizes=np.array(sizes, dtype=np.int64), meta=np.array([max(sizes), c, num_blocks, depth, len(sizes)]),
+                masked_cstn_emb1=me1.tensor.rename(None).detach().numpy(), loss_mean=np.float64(loss.item()))
+    for i in range(len(sizes)):
+        arrs[f"W1/{i}"] = W1[i].numpy().astype(np.uint8)
+        arrs[f"W2/{i}"] = W2[i].numpy().astype(np.uint8)
+        arrs[f"emb1/{i}"] = per1[i].detach().numpy()
+    for k, p_ in model.named_parameters():
+        arrs["grad/" + k] = p_.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(name, "loss", float(loss))
+
+
+def lap_case(name, sources):
+    """accuracy_linear_assignment (toolbox/metrics.py:92-116) of the reference on the scores already stored in
+    other fixtures -- the reference's default metric had no golden before."""
+    arrs = {}
+    for src in sources:
+        z = np.load(os.path.join(OUT, src + ".npz"))
+        scores = torch.from_numpy(z["scores"])
+        arrs[src + "/acc_lap"] = np.array(accuracy_linear_assignment(scores), dtype=np.int64)
+        arrs[src + "/acc_lap_each"] = np.array(accuracy_linear_assignment(scores, aggregate_score=False))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(name, {k: v.tolist() for k, v in arrs.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        # fixtures added in round 2 (the round-1 files are left byte-identical)
+        lap_case("lap_acc", ["cfg1_er50_c32", "cfg3_reg40_c64", "tiny_er12_c8"])
+        ragged_cstn_case("ragged_cstn_c16", [9, 14, 11, 6, 20], 0.4, 0.1, c=16, num_blocks=2, depth=2)
+        headline_case("cfg2_er200_c32", "ErdosRenyi", 200, 0.2, 0.1, pairs=1, c=32, num_blocks=4, depth=3,
+                      perturb=True, with_grads=True)
+        headline_case("cfg3_reg500_c64", "Regular", 500, 0.2, 0.1, pairs=1, c=64, num_blocks=4, depth=3,
+                      perturb=False, with_grads=False)
+        trained_case("trained_er50_c32", 50, 0.2, 0.05, c=32, num_blocks=4, depth=3, steps=700, batch=16, eval_pairs=8)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "trained":
+        trained_case("trained_er50_c32", 50, 0.2, 0.05, c=32, num_blocks=4, depth=3, steps=700, batch=16, eval_pairs=8)
+        sys.exit(0)
     # cfg1 (BASELINE.json configs[0]) at reduced pair count: default_config arch, ER n=50 p=0.2 noise 0.1
     dense_case("cfg1_er50_c32", "ErdosRenyi", 50, 0.2, 0.1, pairs=4, c=32, num_blocks=4, depth=3)
     # headline architecture (C=64, 4 blocks) on small regular graphs

@@ -104,8 +104,11 @@ def test_fp32_model_matches_reference(name):
     # argmax / accuracy parity on the reference's own scores (bit-identical inputs => identical counts)
     ref_scores = torch.from_numpy(z["scores"]).to(DEV)
     assert list(accuracy_max(ref_scores)) == list(z["acc"])
-    lap = accuracy_linear_assignment(ref_scores)
-    assert lap[1] == int(z["acc"][1]) and 0 <= lap[0] <= lap[1]
+    # the reference's default metric (trainers.py:53,74): device LAP == the reference's scipy result on these scores
+    lap_ref = load_golden("lap_acc")
+    assert list(accuracy_linear_assignment(ref_scores)) == list(lap_ref[name + "/acc_lap"])
+    each = accuracy_linear_assignment(ref_scores, aggregate_score=False)
+    assert np.allclose(each, lap_ref[name + "/acc_lap_each"])
 
 
 def test_ragged_batch_matches_per_graph_reference():
@@ -211,3 +214,39 @@ def test_features_from_adjacency_matches_reference_representation():
     assert torch.equal(out.cpu(), ref)
     dense = dg.adjacency_batch_to_tensor_representation(adj[1:2, :64, :64].contiguous().to(DEV))
     assert torch.equal(dense[0].cpu(), graphs[1])
+
+
+@pytest.mark.parametrize("n,sizes", [(12, None), (50, None), (200, None), (64, [64, 1, 33, 2]), (500, [500, 257])])
+def test_device_linear_assignment_equals_scipy(n, sizes):
+    """fgnn_lap_fwd: identical assignment and optimal cost to scipy.optimize.linear_sum_assignment
+    on -log_softmax(scores), the reference's call (toolbox/metrics.py:100-106); padded rows report -1."""
+    from scipy.optimize import linear_sum_assignment
+    from graph_neural_net_b200.toolbox.metrics import linear_assignment
+    gen = torch.Generator().manual_seed(n)
+    G = len(sizes) if sizes else 3
+    scores = torch.randn((G, n, n), generator=gen) * 3
+    scores[0] += 4 * torch.eye(n)                      # one graph with a strong diagonal (trained-like margins)
+    x = scores.to(DEV)
+    if sizes:
+        x = mt.from_list([scores[i, :s, :s] for i, s in enumerate(sizes)], dims=(0, 1)).to(DEV)
+    cols, correct, cost = linear_assignment(x)
+    cols, correct, cost = cols.cpu().numpy(), correct.cpu().numpy(), cost.cpu().numpy()
+    for g in range(G):
+        m = sizes[g] if sizes else n
+        ref_cost_mat = -torch.log_softmax(scores[g, :m, :m], -1).numpy().astype(np.float64)
+        rows, preds = linear_sum_assignment(ref_cost_mat)
+        assert np.array_equal(cols[g, :m], preds), g
+        assert np.all(cols[g, m:] == -1)
+        assert correct[g] == int(np.sum(preds == np.arange(m)))
+        raw = -scores[g, :m, :m].numpy().astype(np.float64)
+        assert abs(cost[g] - raw[rows, preds].sum()) < 1e-6 * max(1.0, abs(cost[g]))
+
+
+def test_lap_on_trained_model_scores_matches_reference():
+    z = load_golden("trained_er50_c32")
+    from graph_neural_net_b200.toolbox.metrics import linear_assignment
+    scores = torch.from_numpy(z["scores"]).to(DEV)
+    cols, correct, _ = linear_assignment(scores)
+    assert np.array_equal(cols.cpu().numpy(), z["lap_preds"])
+    assert list(accuracy_linear_assignment(scores)) == list(z["acc_lap"])
+    assert list(accuracy_max(scores)) == list(z["acc"])
