@@ -28,7 +28,7 @@ def accuracy_max(weights, labels=None, aggregate_score=True):
 def linear_assignment(rawscores):
     """Optimal matchings of a batch on the device (fgnn_lap_fwd): -> (col_of_row (B,N) int32 with -1 in padded rows,
     correct (B,) int32, total_cost (B,) float64).  One CTA per graph runs the shortest-augmenting-path algorithm scipy
-    uses, in double precision, on cost = -scores."""
+    uses, in double precision with scipy's tie rule, on cost = -log_softmax(scores) formed in the kernel."""
     import ctypes as C
     from .. import _lib as L
     scores, n_dev, _ = _as_batch(rawscores)
@@ -45,9 +45,8 @@ def linear_assignment(rawscores):
 
 
 def accuracy_linear_assignment(rawscores, labels=None, aggregate_score=True):
-    """Hungarian matching accuracy (reference toolbox/metrics.py:92-116) computed on the device: log_softmax is a
-    per-row shift, which does not change the optimal assignment, so the raw scores are matched directly; only
-    the per-graph hit counts (B int32) travel to the host.  `labels` (a list of per-graph index arrays) compares
+    """Hungarian matching accuracy (reference toolbox/metrics.py:92-116) computed on the device on
+    -log_softmax(scores) as the reference does; only the per-graph hit counts (B int32) travel to the host.  `labels` (a list of per-graph index arrays) compares
     the device matching with them on the host, as the reference does."""
     scores, n_dev, sizes = _as_batch(rawscores)
     cols, correct, _ = linear_assignment(rawscores)

