@@ -148,8 +148,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (profiling runs only)")
     ap.add_argument("--train", action="store_true",
-                    help="time the fp32 data-parallel TRAINING step (fwd + bwd + flat all-reduce + Adam) instead of "
-                         "the forward; secondary line for configs[1]/[4], not the headline")
+                    help="time the data-parallel TRAINING step (fwd + bwd + flat all-reduce + Adam) in --precision "
+                         "instead of the forward; secondary line for configs[1]/[4], not the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = WORKLOADS[args.workload]
@@ -186,7 +186,6 @@ def main():
 
     if args.train:
         from graph_neural_net_b200.training import train_step
-        model.set_precision("fp32")
         opt = model.configure_optimizers()["optimizer"]
         x1_h, x2_h = make_inputs(cfg, pairs, seed=100 + rank)
         b1, b2 = {"input": x1_h.to(dev)}, {"input": x2_h.to(dev)}
@@ -211,8 +210,9 @@ def main():
             print(json.dumps({"metric": "graph-pairs/sec 2-FGNN siamese training step (fwd+bwd+allreduce+Adam)",
                               "value": pairs * world * args.steps / (ms / 1e3), "unit": "pairs/s", "n_gpus": world,
                               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                              "data": "synthetic", "final_loss": loss,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision],
+                              "data": "synthetic", "final_loss": loss, "gpu_launches": int(lib.fgnn_launch_count()),
                               "config": {"workload": args.workload + "+train", "n": cfg["n"], "width": cfg["c"],
                                          "pairs_per_gpu": pairs, "collective": "one flat fp32 all-reduce per step"}}),
                   flush=True)

@@ -43,6 +43,14 @@ class EmbedParams(C.Structure):
     _fields_ = [("num_blocks", C.c_int32), ("block", BlockParams * FGNN_MAX_BLOCKS)]
 
 
+class BlockGrads(C.Structure):
+    _fields_ = [("mlp1", MlpGrads), ("mlp2", MlpGrads), ("mlp3", MlpGrads)]
+
+
+class EmbedGrads(C.Structure):
+    _fields_ = [("num_blocks", C.c_int32), ("block", BlockGrads * FGNN_MAX_BLOCKS)]
+
+
 class FgnnError(RuntimeError):
     pass
 
@@ -76,6 +84,9 @@ _SIGNATURES = {
     "fgnn_embed_workspace_bytes": (_sz, [C.POINTER(EmbedParams), _i32, _i32, _i32]),
     "fgnn_embed_fwd": (C.c_int, [C.POINTER(EmbedParams), _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "fgnn_embed_fwd_adjacency_u8": (C.c_int, [C.POINTER(EmbedParams), _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fgnn_embed_train_workspace_bytes": (_sz, [C.POINTER(EmbedParams), _i32, _i32, _i32]),
+    "fgnn_embed_fwd_train": (C.c_int, [C.POINTER(EmbedParams), _i32, _vp, _vp, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "fgnn_embed_bwd": (C.c_int, [C.POINTER(EmbedParams), C.POINTER(EmbedGrads), _i32, _vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fgnn_debug_dump_timing": (None, []),
     "fgnn_profile_enable": (None, [C.c_int]),
     "fgnn_profile_reset": (None, []),
@@ -148,6 +159,14 @@ def workspace(device, nbytes: int) -> torch.Tensor:
         buf = raw[off:off + raw.numel() - 1024]
         _workspaces[key] = buf
     return buf
+
+
+def private_workspace(device, nbytes: int) -> torch.Tensor:
+    """A 1 KiB-aligned uint8 tensor of nbytes that is NOT shared with other calls (the 16-bit training forward keeps
+    its activations there until backward)."""
+    raw = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % 1024
+    return raw[off:off + int(nbytes)]
 
 
 def release_workspaces():

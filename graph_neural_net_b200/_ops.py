@@ -340,3 +340,106 @@ def embed_fwd_adjacency(params: L.EmbedParams, precision: int, adj: torch.Tensor
                                             L.ptr(ws), ws.numel(), L.stream_ptr(adj.device)),
             "fgnn_embed_fwd_adjacency_u8")
     return emb
+
+
+def embed_params_from_flat(spec, flat, keep) -> L.EmbedParams:
+    """spec: per block a 3-tuple of (depth, eps, constant_n, has_gn) for mlp1, mlp2, mlp3; flat: the tensors in the
+    order [weights[0..d-1], biases[0..d-1], (gn.weight, gn.bias)] per MLP."""
+    p = L.EmbedParams()
+    p.num_blocks = len(spec)
+    it = iter(flat)
+    for i, trio in enumerate(spec):
+        for name, (depth, eps, cst, has_gn) in zip(("mlp1", "mlp2", "mlp3"), trio):
+            ws = [next(it) for _ in range(depth)]
+            bs = [next(it) for _ in range(depth)]
+            gw, gb = (next(it), next(it)) if has_gn else (None, None)
+            setattr(p.block[i], name, make_mlp_params(ws, bs, gw, gb, eps, keep, cst))
+    return p
+
+
+class GradScale:
+    """Loss scale of the 16-bit backward, the reference's AMP GradScaler in power-of-two form (Lightning precision=16,
+    commander_explore.py:120): fgnn_embed_bwd scales max |d emb| to 2^log2; a step whose gradients overflowed is
+    skipped and log2 is lowered by `backoff`; after `growth_interval` clean steps it is raised by one again."""
+    log2 = 9
+    max_log2 = 9
+    min_log2 = -24
+    backoff = 3
+    growth_interval = 200
+    _good = 0
+
+    @classmethod
+    def update(cls, found_inf: bool):
+        if found_inf:
+            cls.log2 = max(cls.min_log2, cls.log2 - cls.backoff)
+            cls._good = 0
+        else:
+            cls._good += 1
+            if cls._good >= cls.growth_interval and cls.log2 < cls.max_log2:
+                cls.log2 += 1
+                cls._good = 0
+
+
+class EmbedTrainFunction(torch.autograd.Function):
+    """node_embedding forward + backward in a 16-bit precision with every contraction on tcgen05
+    (fgnn_embed_fwd_train / fgnn_embed_bwd): what autograd does to Network.forward under the reference's
+    precision=16 trainer (models/trainers.py:70-76, commander_explore.py:120-123).  The forward's workspace holds the
+    activations until backward; parameter gradients come back in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, n_dev, spec, precision, c_out, *flat):
+        lib = L.get_lib()
+        x = L.require_cuda_f32(x, "input")
+        G, _, N, M = x.shape
+        if N != M:
+            raise L.FgnnError("input must be (B,F,N,N)")
+        keep = []
+        params = embed_params_from_flat(spec, flat, keep)
+        nbytes = lib.fgnn_embed_train_workspace_bytes(C.byref(params), precision, G, N)
+        if nbytes == 0:
+            raise L.FgnnError("fgnn_embed_train_workspace_bytes returned 0: " + lib.fgnn_last_error().decode())
+        ws = L.private_workspace(x.device, nbytes)
+        emb = torch.empty((G, c_out, N), device=x.device, dtype=torch.float32)
+        L.check(lib.fgnn_embed_fwd_train(C.byref(params), precision, L.ptr(x), L.ptr(emb), G, N, _npg(n_dev, G),
+                                         L.ptr(ws), ws.numel(), L.stream_ptr(x.device)), "fgnn_embed_fwd_train")
+        ctx.ws, ctx.spec, ctx.precision, ctx.shape = ws, spec, precision, (G, N)
+        ctx.has_n = n_dev is not None
+        ctx.save_for_backward(n_dev if n_dev is not None else torch.empty(0), *flat)
+        return emb
+
+    @staticmethod
+    def backward(ctx, demb):
+        lib = L.get_lib()
+        n_dev, *flat = ctx.saved_tensors
+        n_dev = n_dev if ctx.has_n else None
+        G, N = ctx.shape
+        keep = []
+        params = embed_params_from_flat(ctx.spec, flat, keep)
+        grads = L.EmbedGrads()
+        grads.num_blocks = len(ctx.spec)
+        out = []
+        it = iter(flat)
+        for i, trio in enumerate(ctx.spec):
+            for name, (depth, eps, cst, has_gn) in zip(("mlp1", "mlp2", "mlp3"), trio):
+                mg = getattr(grads.block[i], name)
+                ws_ = [next(it) for _ in range(depth)]
+                bs_ = [next(it) for _ in range(depth)]
+                gws = [torch.zeros(w.shape[0], w.numel() // w.shape[0], device=demb.device, dtype=torch.float32) for w in ws_]
+                gbs = [torch.zeros(w.shape[0], device=demb.device, dtype=torch.float32) if b is not None else None
+                       for w, b in zip(ws_, bs_)]
+                for k in range(depth):
+                    mg.w[k] = gws[k].data_ptr()
+                    mg.b[k] = gbs[k].data_ptr() if gbs[k] is not None else None
+                out += [g.reshape(w.shape) for g, w in zip(gws, ws_)] + gbs
+                if has_gn:
+                    gw_, gb_ = next(it), next(it)
+                    dgw = torch.zeros(gw_.numel(), device=demb.device, dtype=torch.float32)
+                    dgb = torch.zeros(gb_.numel(), device=demb.device, dtype=torch.float32)
+                    mg.gn_w, mg.gn_b = dgw.data_ptr(), dgb.data_ptr()
+                    out += [dgw.reshape(gw_.shape), dgb.reshape(gb_.shape)]
+        demb = L.require_cuda_f32(demb, "d emb")
+        ws = ctx.ws
+        L.check(lib.fgnn_embed_bwd(C.byref(params), C.byref(grads), ctx.precision, L.ptr(demb), GradScale.log2, G, N, _npg(n_dev, G),
+                                   L.ptr(ws), ws.numel(), L.stream_ptr(demb.device)), "fgnn_embed_bwd")
+        ctx.ws = None
+        return (None, None, None, None, None, *out)

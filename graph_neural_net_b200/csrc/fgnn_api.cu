@@ -276,6 +276,37 @@ int fgnn_embed_fwd_adjacency_u8(const fgnn_embed_params* p, int32_t precision, c
                                  (cudaStream_t)stream);
 }
 
+size_t fgnn_embed_train_workspace_bytes(const fgnn_embed_params* p, int32_t precision, int32_t G, int32_t N) {
+  if (!p || p->num_blocks < 1 || p->num_blocks > FGNN_MAX_BLOCKS || G < 1 || N < 1) return 0;
+  if (precision != FGNN_BF16 && precision != FGNN_FP16) return 0;
+  return tc::embed_train_workspace_bytes(*p, G, N);
+}
+
+int fgnn_embed_fwd_train(const fgnn_embed_params* p, int32_t precision, const float* x, float* emb, int32_t G,
+                         int32_t N, const int32_t* n_per_graph, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (int e = check_embed(p, G, N)) return e;
+  FGNN_CHECK_ARG(x && emb && workspace, "null pointer");
+  return tc::embed_fwd_train(*p, precision, x, emb, G, N, n_per_graph, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int fgnn_embed_bwd(const fgnn_embed_params* p, const fgnn_embed_grads* grads, int32_t precision, const float* demb,
+                   int32_t grad_scale_log2, int32_t G, int32_t N, const int32_t* n_per_graph, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (int e = check_embed(p, G, N)) return e;
+  FGNN_CHECK_ARG(grads && demb && workspace, "null pointer");
+  FGNN_CHECK_ARG(grads->num_blocks == p->num_blocks, "grads describe %d blocks, params %d", grads->num_blocks, p->num_blocks);
+  for (int b = 0; b < p->num_blocks; ++b) {
+    const fgnn_mlp_params* mp[3] = {&p->block[b].mlp1, &p->block[b].mlp2, &p->block[b].mlp3};
+    const fgnn_mlp_grads* mg[3] = {&grads->block[b].mlp1, &grads->block[b].mlp2, &grads->block[b].mlp3};
+    for (int m = 0; m < 3; ++m)
+      for (int l = 0; l < mp[m]->depth; ++l)
+        FGNN_CHECK_ARG(mg[m]->w[l] != nullptr, "block %d mlp%d: missing weight-gradient buffer of layer %d", b, m + 1, l);
+  }
+  return tc::embed_bwd(*p, *grads, precision, demb, grad_scale_log2, G, N, n_per_graph, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+
 size_t fgnn_debug_tc_matmul_workspace_bytes(int32_t G, int32_t C, int32_t N) {
   return tc::debug_matmul_workspace_bytes(G, C, N);
 }

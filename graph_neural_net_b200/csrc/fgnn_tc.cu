@@ -255,6 +255,7 @@ struct CoefArgs {
   int constant_n[2];
   int nmlp, C, N;
   const int32_t* n_per_graph;
+  float* gnstat[2];   // training: [G][C][4] = {mean, 1 / (var + eps), 1 / (2 sqrt(n (var + eps))), 0} kept for backward (or null)
 };
 __global__ void finalize_coef_kernel(CoefArgs a, int total) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,6 +272,13 @@ __global__ void finalize_coef_kernel(CoefArgs a, int total) {
   const double sc = (double)(a.gw[m] ? a.gw[m][c] : 1.f) / (2.0 * sqrt((double)(a.constant_n[m] ? a.N : n) * (var + (double)a.eps[m])));
   a.coef[m][((long)g * a.C + c) * 2] = (float)sc;
   a.coef[m][((long)g * a.C + c) * 2 + 1] = (float)((double)(a.gb[m] ? a.gb[m][c] : 0.f) - sc * mean);
+  if (a.gnstat[m]) {
+    float* gs = a.gnstat[m] + ((long)g * a.C + c) * 4;
+    gs[0] = (float)mean;
+    gs[1] = (float)(1.0 / (var + (double)a.eps[m]));
+    gs[2] = (float)(1.0 / (2.0 * sqrt((double)(a.constant_n[m] ? a.N : n) * (var + (double)a.eps[m]))));
+    gs[3] = 0.f;
+  }
 }
 
 
@@ -346,7 +354,7 @@ struct MlpSmem {
   }
 };
 
-template <typename T, int COUT, int NMLP, bool POOL>
+template <typename T, int COUT, int NMLP, bool POOL, bool RELU_OUT>
 __global__ void __launch_bounds__(480, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
               const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wh,
@@ -782,7 +790,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           }
           const int g = second ? slot_g1 : slot_g0;
           const long gbase = second ? slot_base1 : slot_base0;
-          if (l == 0 && depth > 1 && g != (second ? bias_g1 : bias_g0)) {
+          if (l == 0 && (depth > 1 || RELU_OUT) && g != (second ? bias_g1 : bias_g0)) {
             // first tile of a new graph in this slot (m is fixed per slot: NMLP divides kSlots).  All four warps of the
             // group take this branch at the same item, and the previous tile's layer-0 pass is long finished.
             if (et < COUT) s_bias1[s * COUT + et] = __ldg(args.bias1 + ((long)g * NMLP + m) * COUT + et);
@@ -876,8 +884,33 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
               const uint32_t st_addr = smem_u32(tile) + (uint32_t)(quad >> 1) * (COUT * 128) + (uint32_t)(lane & 7) * 128 +
                                        (uint32_t)(((((quad & 1) << 2) + (lane >> 3)) ^ (lane & 7)) << 4);
               tmem_wait_ld();
+              if constexpr (RELU_OUT) {
+                // training forward, every conv layer is its own depth-1 launch: out = relu(acc + bias), bias of this
+                // thread's channel pair 8u + 2 * (lane % 4), +1 from the slot's folded first-layer bias
+                const float* bsl = s_bias1 + s * COUT + 2 * (lane & 3);     // RELU_OUT launches have depth == 1
+#pragma unroll
+                for (int u = 0; u < COUT / 8; ++u) {
+                  const float2 bb = *reinterpret_cast<const float2*>(bsl + 8 * u);
+                  rl[4 * u] = __float_as_uint(__uint_as_float(rl[4 * u]) + bb.x);
+                  rl[4 * u + 1] = __float_as_uint(__uint_as_float(rl[4 * u + 1]) + bb.y);
+                  rl[4 * u + 2] = __float_as_uint(__uint_as_float(rl[4 * u + 2]) + bb.x);
+                  rl[4 * u + 3] = __float_as_uint(__uint_as_float(rl[4 * u + 3]) + bb.y);
+                  ru[4 * u] = __float_as_uint(__uint_as_float(ru[4 * u]) + bb.x);
+                  ru[4 * u + 1] = __float_as_uint(__uint_as_float(ru[4 * u + 1]) + bb.y);
+                  ru[4 * u + 2] = __float_as_uint(__uint_as_float(ru[4 * u + 2]) + bb.x);
+                  ru[4 * u + 3] = __float_as_uint(__uint_as_float(ru[4 * u + 3]) + bb.y);
+                }
+              }
 #pragma unroll
               for (int u = 0; u < COUT / 8; ++u) {
+                if constexpr (RELU_OUT) {
+                  const uint32_t w0 = vb[0] ? Elem<T>::pack_relu(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
+                  const uint32_t w1 = vb[1] ? Elem<T>::pack_relu(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
+                  const uint32_t w2 = vb[2] ? Elem<T>::pack_relu(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
+                  const uint32_t w3 = vb[3] ? Elem<T>::pack_relu(__uint_as_float(ru[4 * u + 2]), __uint_as_float(ru[4 * u + 3])) : fill[3];
+                  stmatrix_x4_trans(st_addr + (uint32_t)u * 1024u, w0, w1, w2, w3);
+                  continue;
+                }
                 const uint32_t w0 = vb[0] ? Elem<T>::pack(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
                 const uint32_t w1 = vb[1] ? Elem<T>::pack(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
                 const uint32_t w2 = vb[2] ? Elem<T>::pack(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
@@ -1288,6 +1321,7 @@ struct MlpLaunch {
   int ones[2];
   double* stat_acc;    // [G][nmlp][COUT][2], zeroed here
   unsigned int* rowenc[2];   // fused max pooling instead of the store (see MlpArgs), or null
+  int relu_out;              // depth-1 launches of the training path: out = relu(conv + bias) instead of the raw accumulator
 };
 
 template <typename T, int COUT, int NMLP>
@@ -1337,12 +1371,15 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   FGNN_CHECK_ARG(smem <= 227 * 1024, "MLP kernel needs %zu bytes of shared memory", smem);
   const bool pool = a.rowenc[0] != nullptr;
   FGNN_CHECK_ARG(!pool || NMLP == 1, "fused pooling is only built for single-MLP launches");
+  FGNN_CHECK_ARG(!L.relu_out || (L.depth == 1 && !pool), "relu_out is a depth-1, non-pooled launch");
   {   // the opt-in is per device and cheap: set on every call
     if (pool) {
       if constexpr (NMLP == 1)
-        FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else if (L.relu_out) {
+      FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
-      FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FGNN_CUDA(cudaFuncSetAttribute(tc_mlp_kernel<T, COUT, NMLP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
   }
   FGNN_CUDA(cudaMemsetAsync(L.stat_acc, 0, (size_t)G * NMLP * COUT * 2 * sizeof(double), st));
@@ -1351,9 +1388,11 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   if (grid < 1) grid = 1;
   prof::begin(prof::kMlp, st);
   if (pool) {
-    if constexpr (NMLP == 1) tc_mlp_kernel<T, COUT, NMLP, true><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+    if constexpr (NMLP == 1) tc_mlp_kernel<T, COUT, NMLP, true, false><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+  } else if (L.relu_out) {
+    tc_mlp_kernel<T, COUT, NMLP, false, true><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
   } else {
-    tc_mlp_kernel<T, COUT, NMLP, false><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+    tc_mlp_kernel<T, COUT, NMLP, false, false><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
   }
   prof::end(prof::kMlp, st);
   FGNN_LAUNCHED();
@@ -1387,6 +1426,10 @@ struct MlpGroup {
   float* coef[2];
   double* stat_acc;
   unsigned int* rowenc[2];   // fused max pooling of this MLP's output instead of storing it (or null)
+  // training path (depth-1 launches, see fgnn_tc_train.cuh)
+  int relu_out;              // out = relu(conv + bias) instead of the raw accumulator
+  int no_coef;               // skip the GraphNorm coefficient finalisation (hidden layers, backward convs)
+  float* gnstat[2];          // statistics kept for backward (or null)
 };
 
 template <typename T>
@@ -1424,7 +1467,9 @@ int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int3
     L.rowenc[m] = M.rowenc[m];
   }
   L.stat_acc = M.stat_acc;
+  L.relu_out = M.relu_out;
   if (int e = launch_mlp<T>(L, G, geo, npg, st)) return e;
+  if (M.no_coef) return FGNN_OK;
   CoefArgs ca{};
   ca.acc = M.stat_acc;
   ca.nmlp = M.nmlp;
@@ -1437,6 +1482,7 @@ int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int3
     ca.gb[m] = M.mp[m]->gn_b;
     ca.eps[m] = M.mp[m]->eps;
     ca.constant_n[m] = M.mp[m]->constant_n;
+    ca.gnstat[m] = M.gnstat[m];
   }
   const int total = G * M.nmlp * C;
   prof::begin(prof::kStats, st);
@@ -1621,7 +1667,38 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, const uint8_t* adj, 
   return FGNN_OK;
 }
 
+#include "fgnn_tc_train.cuh"
+
 }  // namespace
+
+size_t embed_train_workspace_bytes(const fgnn_embed_params& p, int G, int N) {
+  TrainPlan tp;
+  if (make_train_plan(p, G, N, tp)) return 0;
+  Arena ar(nullptr, 0);
+  TrainBuf B;
+  return carve_train(tp, ar, B);
+}
+
+int embed_fwd_train(const fgnn_embed_params& p, int precision, const float* x, float* emb, int G, int N,
+                    const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!fgnn_device_supports_tcgen05())
+    return fail(FGNN_ERR_UNSUPPORTED, "FGNN_BF16/FGNN_FP16 need an sm_100 device (tcgen05); there is no fallback");
+  if (reinterpret_cast<uintptr_t>(ws) & 1023) return fail(FGNN_ERR_INVALID, "workspace must be 1024-byte aligned");
+  if (precision == FGNN_BF16) return embed_fwd_train_t<__nv_bfloat16>(p, x, emb, G, N, n_per_graph, ws, ws_bytes, st);
+  if (precision == FGNN_FP16) return embed_fwd_train_t<__half>(p, x, emb, G, N, n_per_graph, ws, ws_bytes, st);
+  return fail(FGNN_ERR_INVALID, "fgnn_embed_fwd_train is the 16-bit training path (FGNN_BF16 / FGNN_FP16)");
+}
+
+int embed_bwd(const fgnn_embed_params& p, const fgnn_embed_grads& g, int precision, const float* demb, int grad_scale_log2,
+              int G, int N, const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!fgnn_device_supports_tcgen05())
+    return fail(FGNN_ERR_UNSUPPORTED, "FGNN_BF16/FGNN_FP16 need an sm_100 device (tcgen05); there is no fallback");
+  if (reinterpret_cast<uintptr_t>(ws) & 1023) return fail(FGNN_ERR_INVALID, "workspace must be 1024-byte aligned");
+  if (grad_scale_log2 < -24 || grad_scale_log2 > 15) return fail(FGNN_ERR_INVALID, "grad_scale_log2 %d outside [-24, 15]", grad_scale_log2);
+  if (precision == FGNN_BF16) return embed_bwd_t<__nv_bfloat16>(p, g, demb, grad_scale_log2, G, N, n_per_graph, ws, ws_bytes, st);
+  if (precision == FGNN_FP16) return embed_bwd_t<__half>(p, g, demb, grad_scale_log2, G, N, n_per_graph, ws, ws_bytes, st);
+  return fail(FGNN_ERR_INVALID, "fgnn_embed_bwd is the 16-bit training path (FGNN_BF16 / FGNN_FP16)");
+}
 
 size_t embed_workspace_bytes(const fgnn_embed_params& p, int G, int N) {
   Plan pl;

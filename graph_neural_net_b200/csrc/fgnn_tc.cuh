@@ -13,6 +13,13 @@ int embed_fwd(const fgnn_embed_params& p, int precision, const float* x, float* 
 int embed_fwd_adjacency(const fgnn_embed_params& p, int precision, const uint8_t* adj, float* emb, int G, int N,
                         const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// 16-bit training path (fgnn_tc_train.cuh): forward keeping what backward needs in `ws`, and the backward of the stack
+size_t embed_train_workspace_bytes(const fgnn_embed_params& p, int G, int N);
+int embed_fwd_train(const fgnn_embed_params& p, int precision, const float* x, float* emb, int G, int N,
+                    const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
+int embed_bwd(const fgnn_embed_params& p, const fgnn_embed_grads& g, int precision, const float* demb, int grad_scale_log2,
+              int G, int N, const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
+
 size_t debug_matmul_workspace_bytes(int G, int C, int N);
 int debug_matmul(int precision, const float* a, const float* b, float* out, int G, int C, int N,
                  const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -56,6 +56,10 @@ class Siamese_Node_Exp(_Base):
         self.scheduler_step = scheduler_step
         self.lr_stop = lr_stop
 
+    @property
+    def precision(self):
+        return self.node_embedder.precision
+
     def set_precision(self, precision):
         self.node_embedder.set_precision(precision)
         return self

@@ -152,6 +152,37 @@ class Network(nn.Module):
                 setattr(p.block[i], name, mp)
         return p
 
+    def _flat_params(self):
+        """(spec, tensors) of the fused embedder in the order _ops.embed_params_from_flat expects."""
+        spec, flat = [], []
+        for trio in self._fused[2]:
+            row = []
+            for mlp in trio:
+                row.append((len(mlp.convs), float(mlp.gn.eps), bool(mlp.cst_vertices), True))
+                flat += [c.weight for c in mlp.convs] + [c.bias for c in mlp.convs] + [mlp.gn.weight, mlp.gn.bias]
+            spec.append(tuple(row))
+        return spec, flat
+
+    def forward_fused_train(self, x, precision=None):
+        """Differentiable 16-bit embedder (fgnn_embed_fwd_train / fgnn_embed_bwd): x Tensor (B,F,N,N) or MaskedTensor
+        -> (B,C,N) embeddings that carry autograd history to every parameter."""
+        from .layers import _unwrap
+        from ..maskedtensors.maskedtensor import MaskedTensor
+        if self._fused is None:
+            raise L.FgnnError("this Network is not a node_embedding DAG; fused execution unavailable")
+        prec_name = precision or self.precision
+        if prec_name == 'fp32':
+            raise L.FgnnError("forward_fused_train is the 16-bit training path; fp32 trains through the per-operator Functions")
+        plain, n_dev, rewrap = _unwrap(x)
+        spec, flat = self._flat_params()
+        if any(t is None for t in flat):
+            raise L.FgnnError("the fused training path needs conv biases and an affine GraphNorm (the reference's modules)")
+        c_out = self._fused[2][-1][2].convs[-1].weight.shape[0]
+        emb = _ops.EmbedTrainFunction.apply(plain, n_dev, spec, L.PRECISIONS[prec_name], c_out, *flat)
+        if isinstance(x, MaskedTensor):
+            return rewrap(emb, x.tensor.names[:-1])
+        return emb
+
     def forward_fused(self, x, precision=None):
         """One fgnn_embed_fwd call: x Tensor (B,F,N,N) or MaskedTensor -> (B,C,N) embeddings."""
         from .layers import _unwrap
@@ -189,10 +220,9 @@ class Network(nn.Module):
         outputs = dict(inputs)
         if self._fused is not None and self.precision != 'fp32' and self._fused[0] in outputs:
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-                raise NotImplementedError(
-                    "precision=%r is forward-only in this build; run under torch.no_grad() or use "
-                    "set_precision('fp32') for training" % self.precision)
-            outputs[self._fused[1]] = self.forward_fused(outputs[self._fused[0]])
+                outputs[self._fused[1]] = self.forward_fused_train(outputs[self._fused[0]])
+            else:
+                outputs[self._fused[1]] = self.forward_fused(outputs[self._fused[0]])
             return outputs
         for key, (node, ins) in self.graph.items():
             if key not in outputs:                      # nodes supplied by the caller are not recomputed

@@ -70,10 +70,25 @@ def train_step(model, optimizer, x1, x2, group: Optional[dist.ProcessGroup] = No
     local_sum = ce.sum()
     local_sum.backward()                                   # un-normalised: d(sum CE_local)/d theta
     extras = torch.stack((local_sum.detach(), sizes.sum(), correct.sum().to(torch.float32)))
-    ce_all, n_all, ok_all = flat_gradient_allreduce(model.parameters(), extras, group).tolist()
-    inv = 1.0 / max(n_all, 1.0)
+    # fourth extra: 1 if any local gradient is non-finite (fp16 gradient planes overflowed for the current loss scale)
+    bad = torch.zeros((), device=local_sum.device)
     for p in model.parameters():
         if p.grad is not None:
-            p.grad.mul_(inv)                               # loss = sum CE / sum n  (losses.py:12-13, 34)
-    optimizer.step()
+            bad = bad + (~torch.isfinite(p.grad)).any().to(bad.dtype)
+    for p in model.parameters():                           # keep the flat buffer finite so the loss scalars survive the sum
+        if p.grad is not None:
+            torch.nan_to_num_(p.grad, nan=0.0, posinf=0.0, neginf=0.0)
+    extras = torch.cat((extras, bad.reshape(1)))
+    ce_all, n_all, ok_all, bad_all = flat_gradient_allreduce(model.parameters(), extras, group).tolist()
+    inv = 1.0 / max(n_all, 1.0)
+    found_inf = bad_all > 0
+    if getattr(model, "precision", "fp32") != "fp32":
+        _ops.GradScale.update(found_inf)                   # every rank sees the same flag: scales stay in lock step
+    if found_inf:
+        optimizer.zero_grad(set_to_none=True)              # AMP semantics: skip the step, retry with a lower scale
+    else:
+        for p in model.parameters():
+            if p.grad is not None:
+                p.grad.mul_(inv)                           # loss = sum CE / sum n  (losses.py:12-13, 34)
+        optimizer.step()
     return ce_all * inv, int(round(ok_all)), int(round(n_all))

@@ -83,6 +83,15 @@ typedef struct {
   fgnn_block_params block[FGNN_MAX_BLOCKS];
 } fgnn_embed_params;
 
+/* Parameter gradients of the above (same shapes, accumulated into: the caller zeroes them). */
+typedef struct {
+  fgnn_mlp_grads mlp1, mlp2, mlp3;
+} fgnn_block_grads;
+typedef struct {
+  int32_t num_blocks;
+  fgnn_block_grads block[FGNN_MAX_BLOCKS];
+} fgnn_embed_grads;
+
 /* ---- library ---------------------------------------------------------------------------- */
 const char* fgnn_version(void);
 const char* fgnn_last_error(void); /* thread-local text of the last failure */
@@ -186,6 +195,26 @@ int fgnn_embed_fwd(const fgnn_embed_params* p, int32_t precision, const float* x
 int fgnn_embed_fwd_adjacency_u8(const fgnn_embed_params* p, int32_t precision, const uint8_t* adj, float* emb,
                                 int32_t G, int32_t N, const int32_t* n_per_graph, void* workspace,
                                 size_t workspace_bytes, void* stream);
+
+/* 16-bit TRAINING of the embedder: what autograd does to Network.forward under Lightning's precision=16
+ * (models/trainers.py:70-76, commander_explore.py:120-123), with every contraction of both passes on tcgen05.
+ * fgnn_embed_fwd_train computes the same embeddings as fgnn_embed_fwd (FGNN_BF16 / FGNN_FP16) and leaves in
+ * `workspace` what backward needs (hidden activations, pre-norm planes, GraphNorm statistics, pooling arg-max);
+ * fgnn_embed_bwd takes d loss / d emb (G,C,N) fp32 and ACCUMULATES d loss / d parameter into `grads` (fp32, same
+ * shapes as the parameters; the last conv bias of every MLP receives its exact gradient, zero up to rounding, as
+ * in the reference).  16-bit gradient planes carry a power-of-two loss scale: the one that brings max |d emb| into
+ * [2^(grad_scale_log2 - 1), 2^grad_scale_log2), chosen on the device; the parameter gradients come back un-scaled.
+ * As with the reference's AMP GradScaler, fp16 gradient planes can overflow for a given scale: the parameter
+ * gradients are then non-finite and the caller skips the step and lowers grad_scale_log2 (training.py does; 9 is
+ * the default, -24 .. 15 accepted; bf16 never overflows).  The workspace must be the one the forward call filled
+ * (same G, N, parameters), fgnn_embed_train_workspace_bytes(...) bytes, 1024-byte aligned. */
+size_t fgnn_embed_train_workspace_bytes(const fgnn_embed_params* p, int32_t precision, int32_t G, int32_t N);
+int fgnn_embed_fwd_train(const fgnn_embed_params* p, int32_t precision, const float* x, float* emb, int32_t G,
+                         int32_t N, const int32_t* n_per_graph, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int fgnn_embed_bwd(const fgnn_embed_params* p, const fgnn_embed_grads* grads, int32_t precision, const float* demb,
+                   int32_t grad_scale_log2, int32_t G, int32_t N, const int32_t* n_per_graph, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* Number of kernels the last call on this thread launched (bench.py's gpu_launches). */
 int64_t fgnn_launch_count(void);

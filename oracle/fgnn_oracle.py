@@ -314,3 +314,78 @@ def xavier_state_dict(c_in0: int, c: int, num_blocks: int, depth: int, gen: torc
             sd[f"{root}{b}_mlp{j}.gn.bias"] = gb
         ci = co
     return sd
+
+
+# ---- emulation of the 16-bit pipeline's forward numerics (for the training-path tests) -------------------------
+# The 16-bit CUDA path rounds at fixed points: stored planes, per-graph folded first-layer weights,
+# hidden activations and hidden-layer weights are 16-bit; accumulation, biases, GraphNorm statistics / coefficients
+# and the head are fp32.  This restates THAT forward in torch with straight-through rounding, so that autograd
+# gives the exact gradient of the rounded forward.  It is the oracle of the backward kernels' arithmetic: against
+# the fp32 reference gradient a 16-bit forward deviates by several 1e-2 on random-init weights whatever the backward
+# does (the pooling arg-max and the loss gradient move with the forward's rounding: tools/emulate_grad_noise.py).
+def _ste_round(x: Tensor, dt: torch.dtype) -> Tensor:
+    return x + (x.detach().to(dt).to(x.dtype) - x.detach())
+
+
+def emulated16_node_embedding(x: Tensor, sd: StateDict, dt: torch.dtype,
+                              root: str = "node_embedder.ne_bm_block") -> Tensor:
+    """x: (C0,n,n) one graph -> (C,n) embeddings of the 16-bit pipeline (layers.py:126-131,161-162,194-203)."""
+    nb, depth = count_blocks(sd, root)
+    n = x.shape[-1]
+    P = n * n
+    xs = _ste_round(x.reshape(x.shape[0], P), dt)
+    a_prev = torch.ones(x.shape[0], dtype=x.dtype)
+    s_prev = torch.zeros(x.shape[0], dtype=x.dtype)
+
+    def mlp(inputs, pre):
+        w1 = sd[f"{pre}.convs.0.weight"]
+        w1 = w1.reshape(w1.shape[0], -1)
+        b = sd[f"{pre}.convs.0.bias"]
+        acc, off = 0, 0
+        for st, a, s in inputs:
+            ci = st.shape[0]
+            wp = w1[:, off:off + ci]
+            acc = acc + _ste_round(wp * a[None, :], dt) @ st
+            b = b + wp @ s
+            off += ci
+        h = acc + (b[:, None] if depth > 1 else 0)
+        for k in range(1, depth):
+            h = _ste_round(torch.relu(h), dt)
+            wk = sd[f"{pre}.convs.{k}.weight"]
+            h = _ste_round(wk.reshape(wk.shape[0], -1), dt) @ h
+            if k < depth - 1:
+                h = h + sd[f"{pre}.convs.{k}.bias"][:, None]
+        st = _ste_round(h, dt)                       # stored pre-norm planes (the last bias cancels in GraphNorm)
+        mu = st.mean(1)
+        var = (st * st).mean(1) - mu * mu
+        a = sd[f"{pre}.gn.weight"].reshape(-1) / (2 * torch.sqrt(n * (var + 1e-5)))
+        return st, a, sd[f"{pre}.gn.bias"].reshape(-1) - a * mu
+
+    for i in range(1, nb + 1):
+        pre = f"{root}{i}"
+        y1, a1, s1 = mlp([(xs, a_prev, s_prev)], pre + "_mlp1")
+        y2, a2, s2 = mlp([(xs, a_prev, s_prev)], pre + "_mlp2")
+        c = y1.shape[0]
+        Y1, Y2 = y1.reshape(c, n, n), y2.reshape(c, n, n)
+        mult = (a1 * a2)[:, None, None] * torch.matmul(Y1, Y2) + (a1 * s2)[:, None, None] * Y1.sum(2)[:, :, None] \
+            + (s1 * a2)[:, None, None] * Y2.sum(1)[:, None, :] + (s1 * s2 * n)[:, None, None]
+        mult = _ste_round(mult.reshape(c, P), dt)
+        ones, zeros = torch.ones(c, dtype=x.dtype), torch.zeros(c, dtype=x.dtype)
+        xs, a_prev, s_prev = mlp([(mult, ones, zeros), (xs, a_prev, s_prev)], pre + "_mlp3")
+    out = a_prev[:, None, None] * xs.reshape(-1, n, n) + s_prev[:, None, None]
+    return out.max(-1)[0]
+
+
+def emulated16_loss_and_grads(x1: Tensor, x2: Tensor, sd: StateDict, dt: torch.dtype):
+    """(loss 'mean', {name: d loss / d parameter}) of the emulated 16-bit forward with an exact fp32 backward."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    total, rows = 0.0, 0
+    for g in range(x1.shape[0]):
+        e1 = emulated16_node_embedding(x1[g], params, dt)
+        e2 = emulated16_node_embedding(x2[g], params, dt)
+        s = e1.t() @ e2
+        total = total + torch.nn.functional.cross_entropy(s, torch.arange(s.shape[0]), reduction="sum")
+        rows += s.shape[0]
+    loss = total / rows
+    loss.backward()
+    return float(loss.detach()), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}

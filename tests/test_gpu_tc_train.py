@@ -1,0 +1,157 @@
+"""GPU parity tests of the 16-bit TRAINING path (fgnn_embed_fwd_train / fgnn_embed_bwd, tcgen05 backward).
+
+Two oracles, because a 16-bit FORWARD already moves the gradient: on random-init weights the exact gradient of the
+rounded forward differs from the fp32 gradient by 2e-2 .. 1e-1 per parameter tensor in fp16 (the pooling arg-max and
+d loss / d scores follow the forward's rounding; tools/emulate_grad_noise.py, oracle.emulated16_loss_and_grads).
+  (1) backward arithmetic: CUDA gradients vs the EXACT autograd gradient of the emulated 16-bit forward
+      (oracle/fgnn_oracle.py, same rounding points as the kernels).  What remains is the rounding of the 16-bit
+      GRADIENT planes, amplified by the mean / z-component projections of every GraphNorm backward (a small
+      difference of large terms): all parameters together <= 4e-2, the last block's tensors <= 5e-2, any tensor
+      <= 1.2e-1 in fp16 (bias gradients, sums of signed 16-bit values over a plane, are the noisiest);
+  (2) end to end: vs the gradients the UNMODIFIED reference's fp32 autograd produced (tests/golden "grad/*"): the
+      measured envelope (per tensor <= 1.5e-1, all parameters together <= 7e-2, cosine >= 0.995 in fp16).
+Ragged batches: vs the repo's fp32 CUDA operators, themselves pinned to the reference's ragged gradient golden.
+"""
+import numpy as np
+import pytest
+import torch
+
+import graph_neural_net_b200 as pkg
+from graph_neural_net_b200.maskedtensors import maskedtensor as mt
+from graph_neural_net_b200.toolbox.losses import triplet_loss
+from oracle import fgnn_oracle as O
+from tests.helpers import load_golden, state_dict_of, rel_fro
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+# (per tensor, all parameters together, cosine, last block's tensors)
+EMUL_TOL = {"fp16": (1.2e-1, 4e-2, 0.999, 5e-2), "bf16": (4.5e-1, 2e-1, 0.99, 3.5e-1)}   # vs the emulated-forward gradient
+# vs the fp32 reference (fp16 only: a bf16 FORWARD is 1e-1 .. 2.5e-1 off on these random-init networks, DESIGN.md
+# "Precision", and so is every gradient computed from it -- printed, not asserted)
+REF_TOL = {"fp16": (1.5e-1, 7e-2, 0.995, None), "bf16": (1e9, 1e9, -1.0, None)}
+TDT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def feats(W):
+    return torch.stack([O.adjacency_to_features(torch.from_numpy(w.astype(np.float32))) for w in W])
+
+
+def unpack_adj(bits, n):
+    return np.unpackbits(bits, axis=-1)[..., :n]
+
+
+def build_model(z, precision, **extra):
+    n, c, nb, depth, _ = [int(v) for v in z["meta"]]
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=nb,
+                    in_features=c, out_features=c, depth_of_mlp=depth, **extra)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(state_dict_of(z))
+    return model.to(DEV).set_precision(precision)
+
+
+def compare_grads(model, ref, tols, label, depth=3, last_block=None):
+    """ref: name -> array.  The last conv bias of every MLP has a mathematically zero gradient (it cancels in
+    GraphNorm): checked against the scale of the same MLP's first bias gradient."""
+    tol, global_tol, min_cos, last_tol = tols
+    worst, worst_k, worst_last = 0.0, None, 0.0
+    named = dict(model.named_parameters())
+    mine, theirs = [], []
+    for k, p in named.items():
+        g = torch.as_tensor(np.asarray(ref[k]), dtype=torch.float32)
+        assert p.grad is not None, k
+        assert torch.isfinite(p.grad).all(), k
+        if k.endswith(f"convs.{depth - 1}.bias"):
+            scale = float(torch.as_tensor(np.asarray(ref[k.rsplit("convs.", 1)[0] + "convs.0.bias"])).norm())
+            assert float(p.grad.norm()) < 2e-1 * max(scale, 1e-6), (k, float(p.grad.norm()), scale)
+            continue
+        mine.append(p.grad.detach().cpu().flatten())
+        theirs.append(g.flatten())
+        e = rel_fro(p.grad.cpu(), g)
+        if e > worst:
+            worst, worst_k = e, k
+        if last_block is not None and f"block{last_block}_" in k:
+            worst_last = max(worst_last, e)
+    a, b = torch.cat(mine), torch.cat(theirs)
+    glob = float((a - b).norm() / b.norm())
+    cos = float(a @ b / (a.norm() * b.norm()))
+    print(f"PARITY grads {label}: worst per-tensor rel err {worst:.3e} ({worst_k}), all parameters {glob:.3e}, "
+          f"cosine {cos:.5f}, last block {worst_last:.3e}")
+    assert worst < tol, (worst_k, worst)
+    assert glob < global_tol, glob
+    assert cos > min_cos, cos
+    if last_tol is not None and last_block is not None:
+        assert worst_last < last_tol, worst_last
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", ["cfg1_er50_c32", "cfg2_er200_c32"])
+def test_tc_training_gradients_match_reference_autograd(name, prec):
+    z = load_golden(name)
+    n = int(z["meta"][0])
+    model = build_model(z, prec)
+    if "W1" in z:
+        x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    else:
+        x1, x2 = feats(unpack_adj(z["W1_bits"], n)).to(DEV), feats(unpack_adj(z["W2_bits"], n)).to(DEV)
+    scores = model({"input": x1}, {"input": x2})          # grad enabled -> fgnn_embed_fwd_train
+    assert scores.requires_grad
+    loss = triplet_loss("mean")(scores)
+    print(f"{name} {prec}: loss {float(loss.detach()):.6f} vs reference {float(z['loss_mean']):.6f}")
+    assert abs(float(loss.detach()) - float(z["loss_mean"])) < (5e-3 if prec == "fp16" else 5e-2) * max(1.0, abs(float(z["loss_mean"])))
+    # the training forward computes the same embeddings as the inference forward (same rounding points)
+    with torch.no_grad():
+        s_inf = model({"input": x1}, {"input": x2})
+    assert rel_fro(scores.detach().cpu(), s_inf.cpu()) < (2e-3 if prec == "fp16" else 2e-2)
+    loss.backward()
+    depth = int(z["meta"][3])
+    # (1) the backward kernels' arithmetic: exact gradient of the emulated 16-bit forward (CPU autograd)
+    eloss, egrads = O.emulated16_loss_and_grads(x1.cpu(), x2.cpu(), state_dict_of(z), TDT[prec])
+    assert abs(float(loss.detach()) - eloss) < 2e-4 * max(1.0, abs(eloss)), (float(loss.detach()), eloss)
+    ref = {k[5:]: z[k] for k in z if k.startswith("grad/")}
+    nb = int(z["meta"][2])
+    try:
+        compare_grads(model, egrads, EMUL_TOL[prec], f"{name} {prec} vs emulated-16-bit-forward autograd", depth, nb)
+    finally:
+        # (2) end to end against the unmodified reference's fp32 autograd
+        compare_grads(model, ref, REF_TOL[prec], f"{name} {prec} vs reference fp32 autograd", depth, nb)
+
+
+@pytest.mark.parametrize("cst", [False, True])
+def test_tc_training_ragged_gradients_match_fp32_path(cst):
+    """Ragged MaskedTensor batch (in-kernel masking in forward AND backward): fp16 tcgen05 gradients vs the fp32
+    CUDA operators' autograd on the same batch, both settings of constant_n_vertices."""
+    gen = torch.Generator().manual_seed(31)
+    sizes = [50, 23, 37, 64, 130]
+    sd = O.xavier_state_dict(2, 32, 3, 3, gen, randomize_gn=True)
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=3,
+                    in_features=32, out_features=32, depth_of_mlp=3, constant_n_vertices=cst)
+    pairs = [O.synthetic_pair(s, 0.3, 0.1, gen) for s in sizes]
+    grads = {}
+    losses = {}
+    for prec in ("fp32", "fp16"):
+        model = pkg.models.Siamese_Node_Exp(2, dict(node_emb))
+        model.load_state_dict(sd)
+        model = model.to(DEV).set_precision(prec)
+        x1 = mt.from_list([p[0] for p in pairs], dims=(1, 2)).to(DEV)
+        x2 = mt.from_list([p[1] for p in pairs], dims=(1, 2)).to(DEV)
+        scores = model({"input": x1}, {"input": x2})
+        loss = triplet_loss("mean")(scores)
+        loss.backward()
+        losses[prec] = float(loss.detach())
+        grads[prec] = {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters()}
+        last = model
+    assert abs(losses["fp16"] - losses["fp32"]) < 5e-3 * max(1.0, abs(losses["fp32"]))
+    compare_grads(last, grads["fp32"], (3e-1, 8e-2, 0.995, None), f"ragged constant_n={cst} fp16 vs fp32 CUDA", 3)
+
+
+def test_tc_train_step_reduces_loss():
+    """A few Adam steps of training.train_step in fp16 on one batch (world size 1)."""
+    from graph_neural_net_b200.training import train_step
+    z = load_golden("cfg1_er50_c32")
+    model = build_model(z, "fp16")
+    opt = model.configure_optimizers()["optimizer"]
+    x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    losses = [train_step(model, opt, {"input": x1}, {"input": x2})[0] for _ in range(6)]
+    print("fp16 train_step losses", [round(v, 4) for v in losses])
+    assert abs(losses[0] - float(z["loss_mean"])) < 2e-2
+    assert losses[-1] < losses[0]
