@@ -185,8 +185,8 @@ def main():
     loss_fn = triplet_loss()
 
     if args.train:
-        from graph_neural_net_b200.training import train_step
-        opt = model.configure_optimizers()["optimizer"]
+        from graph_neural_net_b200.training import train_step_flat as train_step, FlatAdam
+        opt = FlatAdam(model.parameters(), lr=model.lr)
         x1_h, x2_h = make_inputs(cfg, pairs, seed=100 + rank)
         b1, b2 = {"input": x1_h.to(dev)}, {"input": x2_h.to(dev)}
         for _ in range(args.warmup):

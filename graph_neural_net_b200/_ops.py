@@ -380,6 +380,12 @@ class GradScale:
                 cls._good = 0
 
 
+# Gradient sink of the flat trainer (training.FlatAdam): data_ptr of a parameter -> the fp32 view of the flat gradient
+# buffer that receives its gradient.  fgnn_embed_bwd ACCUMULATES into its output buffers, so the 16-bit backward
+# writes straight into the flat buffer (no per-parameter zeros / adds / copies) and returns no autograd gradient.
+GRAD_SINK = {}
+
+
 class EmbedTrainFunction(torch.autograd.Function):
     """node_embedding forward + backward in a 16-bit precision with every contraction on tcgen05
     (fgnn_embed_fwd_train / fgnn_embed_bwd): what autograd does to Network.forward under the reference's
@@ -424,19 +430,27 @@ class EmbedTrainFunction(torch.autograd.Function):
                 mg = getattr(grads.block[i], name)
                 ws_ = [next(it) for _ in range(depth)]
                 bs_ = [next(it) for _ in range(depth)]
-                gws = [torch.zeros(w.shape[0], w.numel() // w.shape[0], device=demb.device, dtype=torch.float32) for w in ws_]
-                gbs = [torch.zeros(w.shape[0], device=demb.device, dtype=torch.float32) if b is not None else None
-                       for w, b in zip(ws_, bs_)]
+                tensors = ws_ + bs_ + ([next(it), next(it)] if has_gn else [])
+                bufs = []
+                for t in tensors:
+                    if t is None:
+                        bufs.append(None)
+                        out.append(None)
+                        continue
+                    sink = GRAD_SINK.get(t.data_ptr())
+                    if sink is not None and sink.numel() == t.numel():
+                        bufs.append(sink)                 # accumulate in place in the trainer's flat buffer
+                        out.append(None)
+                    else:
+                        g = torch.zeros(t.numel(), device=demb.device, dtype=torch.float32)
+                        bufs.append(g)
+                        out.append(g.reshape(t.shape))
                 for k in range(depth):
-                    mg.w[k] = gws[k].data_ptr()
-                    mg.b[k] = gbs[k].data_ptr() if gbs[k] is not None else None
-                out += [g.reshape(w.shape) for g, w in zip(gws, ws_)] + gbs
+                    mg.w[k] = bufs[k].data_ptr()
+                    mg.b[k] = bufs[depth + k].data_ptr() if bufs[depth + k] is not None else None
                 if has_gn:
-                    gw_, gb_ = next(it), next(it)
-                    dgw = torch.zeros(gw_.numel(), device=demb.device, dtype=torch.float32)
-                    dgb = torch.zeros(gb_.numel(), device=demb.device, dtype=torch.float32)
-                    mg.gn_w, mg.gn_b = dgw.data_ptr(), dgb.data_ptr()
-                    out += [dgw.reshape(gw_.shape), dgb.reshape(gb_.shape)]
+                    mg.gn_w, mg.gn_b = bufs[2 * depth].data_ptr(), bufs[2 * depth + 1].data_ptr()
+                keep += bufs
         demb = L.require_cuda_f32(demb, "d emb")
         ws = ctx.ws
         L.check(lib.fgnn_embed_bwd(C.byref(params), C.byref(grads), ctx.precision, L.ptr(demb), GradScale.log2, G, N, _npg(n_dev, G),

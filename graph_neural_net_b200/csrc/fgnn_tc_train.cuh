@@ -137,11 +137,15 @@ __global__ void gn_param_grad_kernel(const double* __restrict__ acc, const float
   if (dgb) dgb[c] += (float)(sb * inv);
 }
 
-// dz = a dy + beta z + gamma on the valid block, 0 elsewhere (layout C out, covered rows only)
+// dz = a dy + beta z + gamma on the valid block, 0 elsewhere (layout C out, covered rows only);
+// bsum[gc] += sum of the ROUNDED dz (the last conv's bias gradient: zero up to rounding, as in the reference)
 template <typename T>
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const T* __restrict__ dya, const T* __restrict__ dyb, const T* __restrict__ z, int zmode,
-                    const float* __restrict__ bc, T* __restrict__ out, int C, Geo geo, const int32_t* __restrict__ npg) {
+                    const float* __restrict__ bc, T* __restrict__ out, float* __restrict__ bsum, int C, Geo geo,
+                    const int32_t* __restrict__ npg) {
+  __shared__ float s_red[8];
+  float ssum = 0.f;
   const int gc = blockIdx.y, g = gc / C;
   const int n = graph_n(npg, g, geo.N);
   const int rows = rows_cover(npg, g, geo);
@@ -167,8 +171,17 @@ gn_bwd_apply_kernel(const T* __restrict__ dya, const T* __restrict__ dyb, const 
       for (int e = 0; e < 8; ++e)
         if (vm & (1u << e)) r[e] = fmaf(a, d[e], fmaf(be, zz[e], ga));
     }
-    *reinterpret_cast<uint4*>(out + oc) = pack8<T>(r);
+    const uint4 pk = pack8<T>(r);
+    *reinterpret_cast<uint4*>(out + oc) = pk;
+    if (vm) {
+      float rr[8];
+      unpack8<T>(pk, rr);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ssum += rr[e];
+    }
   }
+  const float t = block_sum(ssum, s_red);
+  if (threadIdx.x == 0) atomicAdd(bsum + gc, t);
 }
 
 // ReLU backward in place: pre <- pre * [h > 0]; bsum[gc] += sum of the result (bias gradient of the layer below)
@@ -417,9 +430,13 @@ struct WgradArgs {
   Geo geo;
   const int32_t* n_per_graph;
 };
-constexpr int kWgStages = 4;
-constexpr int kWgStageBytes = 128 * 128 + 128 * 128;   // A: 128 rows x 64 px, B: up to 128 rows x 64 px
-constexpr size_t kWgSmemBytes = (size_t)kWgStages * kWgStageBytes + (2 * kWgStages + 4) * 8 + 16;
+// A stage holds only the rows the tensor maps deliver: co_pad = round_up(co, 8) rows of A (the MMA still reads 128 rows:
+// rows >= co_pad are whatever the ring holds, they only feed accumulator lanes nobody reads) and Nw rows of B.  With
+// 32-channel layers a stage is 8 KB, and the ring is as deep as shared memory allows: the kernel is a pure
+// streaming reduction and needs tens of KB in flight per SM.
+constexpr int kWgMaxStages = 16;
+constexpr size_t kWgRingBytes = 160 * 1024;
+constexpr size_t kWgSmemBytes = kWgRingBytes + 128 * 128 + (2 * kWgMaxStages + 4) * 8 + 16;   // + slack the last stage's 128-row read may touch
 
 template <typename T>
 __global__ void __launch_bounds__(192, 1)
@@ -428,16 +445,19 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   extern __shared__ uint8_t smem_wg[];
   uint8_t* smem = smem_wg;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWgStages * kWgStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgRingBytes + 128 * 128);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kWgStages;
-  uint64_t* tmem_full = bars + 2 * kWgStages;   // [2]
+  uint64_t* empty = bars + kWgMaxStages;
+  uint64_t* tmem_full = bars + 2 * kWgMaxStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   const Geo geo = args.geo;
   const int Nw = args.Nw;
-  const uint32_t stage_tx = 128u * 128u + (uint32_t)Nw * 128u;
+  const int co_pad = (args.co + 7) & ~7;
+  const uint32_t stage_tx = (uint32_t)(co_pad + Nw) * 128u;
+  const uint32_t stage_bytes = (stage_tx + 1023u) & ~1023u;
+  const int kWgStages = min(kWgMaxStages, (int)(kWgRingBytes / stage_bytes));
   const int items = args.G * args.S;
 
   if (threadIdx.x == 0) {
@@ -445,6 +465,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     fence_barrier_init();
   }
+  // rows of a stage the tensor maps never write are read by the 128-row MMA: give them finite contents once
+  for (uint32_t i = threadIdx.x; i < (uint32_t)((kWgRingBytes + 128 * 128) / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
@@ -470,8 +494,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       item_range(item, g, lo, hi);
       for (int st = lo; st < hi; ++st) {
         mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + (size_t)stage * kWgStageBytes;
-        uint8_t* sb = sa + 128 * 128;
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        uint8_t* sb = sa + (size_t)co_pad * 128;
         mbar_arrive_expect_tx_e(&full[stage], stage_tx);
         tma_load_3d_e(sa, &map_a, &full[stage], st * 64, 0, g);
         tma_load_3d_e(sb, &map_b0, &full[stage], st * 64, 0, g);
@@ -482,7 +506,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc(Elem<T>::kFmt, /*A K-major*/ 0, /*B K-major*/ 0, 128, Nw);
     const uint64_t a_d0 = smem_desc_sw128(smem_u32(smem), 16u, 1024u);
-    const uint64_t b_d0 = smem_desc_sw128(smem_u32(smem) + 128 * 128, 16u, 1024u);
+    const uint64_t b_d0 = smem_desc_sw128(smem_u32(smem) + (uint32_t)co_pad * 128u, 16u, 1024u);
     const uint32_t a_lo0 = (uint32_t)a_d0, a_hi = (uint32_t)(a_d0 >> 32);
     const uint32_t b_lo0 = (uint32_t)b_d0, b_hi = (uint32_t)(b_d0 >> 32);
     int stage = 0;
@@ -498,8 +522,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int st = lo; st < hi; ++st) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kWgStageBytes >> 4);
-        const uint32_t b_lo = b_lo0 + (uint32_t)stage * (kWgStageBytes >> 4);
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * (stage_bytes >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)stage * (stage_bytes >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           mma_ss2_e(d_tmem, a_lo + (uint32_t)k * (32u >> 4), a_hi, b_lo + (uint32_t)k * (32u >> 4), b_hi, idesc,
@@ -802,7 +826,7 @@ int launch_wgrad(const T* gplanes, int co, const T* src0, int c0, const T* src1,
   const int k0 = round_up(c0, 16), k1 = src1 ? round_up(c1, 16) : 0;
   FGNN_CHECK_ARG(co <= 128 && k0 + k1 <= 128, "weight-gradient GEMM supports <= 128 channels per side (got %d x %d)", co, k0 + k1);
   CUtensorMap ma, mb0, mb1;
-  if (int e = make_map3(&ma, is_bf16, gplanes, geo.PSC, co, G, geo.PSC, (uint64_t)co * geo.PSC, 64, 128)) return e;
+  if (int e = make_map3(&ma, is_bf16, gplanes, geo.PSC, co, G, geo.PSC, (uint64_t)co * geo.PSC, 64, (co + 7) & ~7)) return e;
   if (int e = make_map3(&mb0, is_bf16, src0, geo.PSC, c0, G, geo.PSC, (uint64_t)c0 * geo.PSC, 64, k0)) return e;
   if (src1) {
     if (int e = make_map3(&mb1, is_bf16, src1, geo.PSC, c1, G, geo.PSC, (uint64_t)c1 * geo.PSC, 64, k1)) return e;
@@ -1148,11 +1172,9 @@ int mlp_bwd(const MlpBwd<T>& a, const TrainPlan& tp, const TrainBuf& B, const in
   FGNN_LAUNCHED();
   gn_param_grad_kernel<<<ceil_div(C, 64), 64, 0, st>>>(B.gacc, a.gnstat, a.gr->gn_w, a.gr->gn_b, B.scale, G, C);
   FGNN_LAUNCHED();
-  gn_bwd_apply_kernel<T><<<pgrid, 256, 0, st>>>(a.dya, a.dyb, a.z, a.zmode, B.bc, a.bufs[0], C, geo, npg);
-  FGNN_LAUNCHED();
   int bi = 0;                                           // bsum[bi] = per-(graph, channel) sum of the current gradient
   FGNN_CUDA(cudaMemsetAsync(B.bsum[bi], 0, (size_t)GC * sizeof(float), st));
-  plane_sum_kernel<T><<<pgrid, 256, 0, st>>>(a.bufs[0], B.bsum[bi], C, geo, npg);
+  gn_bwd_apply_kernel<T><<<pgrid, 256, 0, st>>>(a.dya, a.dyb, a.z, a.zmode, B.bc, a.bufs[0], B.bsum[bi], C, geo, npg);
   FGNN_LAUNCHED();
   prof::end(prof::kStats, st);
   T* curg = a.bufs[0];

@@ -216,6 +216,16 @@ int fgnn_embed_bwd(const fgnn_embed_params* p, const fgnn_embed_grads* grads, in
                    int32_t grad_scale_log2, int32_t G, int32_t N, const int32_t* n_per_graph, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Fused multi-tensor Adam on one flat fp32 buffer: torch.optim.Adam(lr) of configure_optimizers
+ * (models/trainers.py:92-104; betas, eps, weight_decay as given, no amsgrad) for all n entries in one launch.
+ * p, g, m, v: parameters, gradients, first / second moments (n floats each, device); step >= 1 is the bias-correction
+ * step.  grad_div (device scalar or NULL): gradients are divided by max(*grad_div, 1) -- the global row count of the
+ * loss after the data-parallel all-reduce (toolbox/losses.py:32-34); skip_flag (device scalar or NULL): if
+ * *skip_flag > 0 nothing is updated (a rank's 16-bit gradients overflowed: AMP's skipped step). */
+int fgnn_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int32_t step, const float* grad_div, const float* skip_flag,
+                       void* stream);
+
 /* Number of kernels the last call on this thread launched (bench.py's gpu_launches). */
 int64_t fgnn_launch_count(void);
 void fgnn_reset_launch_count(void);

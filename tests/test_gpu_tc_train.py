@@ -155,3 +155,47 @@ def test_tc_train_step_reduces_loss():
     print("fp16 train_step losses", [round(v, 4) for v in losses])
     assert abs(losses[0] - float(z["loss_mean"])) < 2e-2
     assert losses[-1] < losses[0]
+
+
+def test_flat_adam_matches_torch_adam():
+    """the fused flat Adam (one launch over one flat buffer, gradient sink, device-side divisor)
+    follows torch.optim.Adam -- the reference's configure_optimizers (models/trainers.py:92-104) -- step for step."""
+    from graph_neural_net_b200.training import train_step, train_step_flat, FlatAdam
+    z = load_golden("tiny_er12_c8")
+    n, c, nb, depth, _ = [int(v) for v in z["meta"]]
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=nb,
+                    in_features=c, out_features=c, depth_of_mlp=depth)
+    x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    models = []
+    for _ in range(2):
+        m = pkg.models.Siamese_Node_Exp(2, dict(node_emb))
+        m.load_state_dict(state_dict_of(z))
+        models.append(m.to(DEV).set_precision("fp32"))
+    opt_a = models[0].configure_optimizers()["optimizer"]
+    opt_b = FlatAdam(models[1].parameters(), lr=models[1].lr)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt_b, factor=0.5, patience=0, min_lr=1e-5)   # drives the flat optimiser too
+    for it in range(4):
+        la = train_step(models[0], opt_a, {"input": x1}, {"input": x2})
+        lb = train_step_flat(models[1], opt_b, {"input": x1}, {"input": x2})
+        assert abs(la[0] - lb[0]) < 1e-5 * max(1.0, abs(la[0])), (it, la, lb)
+        assert la[1:] == lb[1:]
+    for (ka, pa), (kb, pb) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        assert ka == kb
+        if ka.endswith(f"convs.{depth - 1}.bias"):
+            continue        # gradient is rounding noise around zero (cancels in GraphNorm): Adam's +-lr steps follow its sign
+        assert float((pa - pb).abs().max()) < 2e-6 * max(1.0, float(pa.abs().max())), ka
+    sched.step(1.0)
+    sched.step(2.0)                                    # no improvement, patience 0 -> lr halves
+    assert abs(opt_b.param_groups[0]["lr"] - 0.5 * models[1].lr) < 1e-12
+
+
+def test_tc_train_step_flat_reduces_loss():
+    from graph_neural_net_b200.training import train_step_flat, FlatAdam
+    z = load_golden("cfg1_er50_c32")
+    model = build_model(z, "fp16")
+    opt = FlatAdam(model.parameters(), lr=model.lr)
+    x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    losses = [train_step_flat(model, opt, {"input": x1}, {"input": x2})[0] for _ in range(6)]
+    print("fp16 train_step_flat losses", [round(v, 4) for v in losses])
+    assert abs(losses[0] - float(z["loss_mean"])) < 2e-2
+    assert losses[-1] < losses[0]
