@@ -100,6 +100,156 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
 
 
+def er_pairs_on_device(pairs, n, p, noise, dev, seed):
+    """Erdos-Renyi pairs of the reference's generator (loaders/data_generator.py:39-44, 79-87:
+    W_noise = W (1 - N1) + (1 - W) N2, N1 ~ ER(noise), N2 ~ ER(p noise / (1 - p))) drawn with torch on the GPU
+    (distributional stand-in used by the secondary lines only) -> two (pairs, 2, n, n) fp32 feature tensors."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+
+    def er(prob):
+        u = torch.rand((pairs, n, n), device=dev, generator=g)
+        a = torch.triu((u < prob).float(), 1)
+        return a + a.transpose(1, 2)
+
+    W = er(p)
+    Wn = W * (1 - er(noise)) + (1 - W) * er(p * noise / (1 - p))
+
+    def feats(A):
+        return torch.stack((A, torch.diag_embed(A.sum(2))), dim=1).contiguous()
+    return feats(W), feats(Wn)
+
+
+def _time_steps(fn, steps, warmup, dev, world):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, out
+
+
+def run_secondaries(pkg, dev, rank, world, precision):
+    """Secondary lines for the other BASELINE.json configs (short runs, same timing rules: warm-up >= 3, CUDA events,
+    max over ranks).  N = 1: cfg1 / cfg2 forward, cfg2 training step, cfg4 ragged forward and training step.
+    N > 1: the cfg5 data-parallel training step with its flat all-reduce, and the fixed-512-pair strong-scaling point."""
+    import numpy as np
+    import torch.distributed as dist
+    from oracle import fgnn_oracle as O
+    from graph_neural_net_b200 import _ops
+    from graph_neural_net_b200.maskedtensors import maskedtensor as mt
+    from graph_neural_net_b200.toolbox.losses import triplet_loss
+    from graph_neural_net_b200.training import train_step_flat, FlatAdam
+    prec = precision if precision != "fp32" else "fp16"
+    dt = {"fp16": "f16", "bf16": "bf16"}[prec]
+    out = {}
+
+    def build(c, blocks=4, depth=3, **extra):
+        node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=blocks,
+                        in_features=c, out_features=c, depth_of_mlp=depth, **extra)
+        model = pkg.models.Siamese_Node_Exp(2, node_emb)
+        model.load_state_dict(O.xavier_state_dict(2, c, blocks, depth, torch.Generator().manual_seed(3787)))
+        return model.to(dev)
+
+    def fwd_line(model, x1, x2, p, flops, steps=5):
+        model.set_precision(p)
+        loss_fn = triplet_loss()
+
+        def step():
+            with torch.no_grad():
+                return loss_fn(model(x1, x2))
+        ms, _ = _time_steps(step, steps, 3, dev, world)
+        pairs = (x1["input"].shape[0] if not isinstance(x1["input"], mt.MaskedTensor) else len(x1["input"])) * world
+        return {"value": pairs * steps / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms / steps, "dtype": {"fp32": "f32"}.get(p, dt),
+                "tflops": flops * world * steps / (ms / 1e3) / 1e12}
+
+    def train_line(model, x1, x2, flops_fwd, steps=4):
+        model.set_precision(prec)
+        opt = FlatAdam(model.parameters(), lr=model.lr)
+        ms, res = _time_steps(lambda: train_step_flat(model, opt, x1, x2), steps, 3, dev, world)
+        pairs = (x1["input"].shape[0] if not isinstance(x1["input"], mt.MaskedTensor) else len(x1["input"])) * world
+        return {"value": pairs * steps / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms / steps, "dtype": dt,
+                "tflops": 3 * flops_fwd * world * steps / (ms / 1e3) / 1e12, "final_loss": res[0],
+                "what": "fwd + tcgen05 bwd + one flat all-reduce + fused flat Adam (fgnn_embed_fwd_train / fgnn_embed_bwd)"}
+
+    if world == 1:
+        m32 = build(32)
+        a, b = er_pairs_on_device(32, 50, 0.2, 0.1, dev, 1)
+        f1 = O.flops_per_pair(50, 32) * 32
+        out["cfg1_er_n50_c32_b32_fwd"] = {"fp32": fwd_line(m32, {"input": a}, {"input": b}, "fp32", f1),
+                                          prec: fwd_line(m32, {"input": a}, {"input": b}, prec, f1)}
+        a, b = er_pairs_on_device(128, 200, 0.2, 0.1, dev, 2)
+        f2 = O.flops_per_pair(200, 32) * 128
+        out["cfg2_er_n200_c32_b128_fwd"] = fwd_line(m32, {"input": a}, {"input": b}, prec, f2)
+        out["cfg2_er_n200_c32_b128_train"] = train_line(build(32), {"input": a}, {"input": b}, f2)
+        del a, b
+        # cfg4: ragged MaskedTensor batch, n_b ~ UniformInt[50, 1000] (numpy default_rng(3787)), in-kernel masking
+        rng = np.random.default_rng(3787)
+        sizes = [int(v) for v in rng.integers(50, 1001, size=16)]
+        g1, g2 = [], []
+        for i, nb in enumerate(sizes):
+            a, b = er_pairs_on_device(1, nb, 0.2, 0.1, dev, 100 + i)
+            g1.append(a[0].cpu())
+            g2.append(b[0].cpu())
+        f4 = sum(O.flops_per_pair(nb, 32) for nb in sizes)
+        mr = build(32, constant_n_vertices=False)
+        x1 = {"input": mt.from_list(g1, dims=(1, 2)).to(dev)}
+        x2 = {"input": mt.from_list(g2, dims=(1, 2)).to(dev)}
+        line = fwd_line(mr, x1, x2, prec, f4, steps=3)
+        line["sizes"] = sizes
+        line["flops"] = "sum over graphs of the SURVEY 8(d) formula at each n_b (never at Nmax)"
+        out["cfg4_ragged_n50_1000_c32_b16_fwd"] = line
+        k = 4
+        x1 = {"input": mt.from_list(g1[:k], dims=(1, 2)).to(dev)}
+        x2 = {"input": mt.from_list(g2[:k], dims=(1, 2)).to(dev)}
+        tl = train_line(build(32, constant_n_vertices=False), x1, x2, sum(O.flops_per_pair(nb, 32) for nb in sizes[:k]), steps=3)
+        tl["sizes"] = sizes[:k]
+        out["cfg4_ragged_c32_b4_train"] = tl
+        pkg._lib.release_workspaces()
+        torch.cuda.empty_cache()
+    else:
+        # cfg5: data-parallel training step, ER n=100, 128 pairs per GPU (global 128 N), ONE flat all-reduce per step
+        a, b = er_pairs_on_device(128, 100, 0.2, 0.1, dev, 50 + rank)
+        model = build(32)
+        f5 = O.flops_per_pair(100, 32) * 128
+        tl = train_line(model, {"input": a}, {"input": b}, f5, steps=5)
+        nparam = sum(p.numel() for p in model.parameters())
+        buf = torch.zeros(nparam + 4, device=dev)
+        ms_ar, _ = _time_steps(lambda: dist.all_reduce(buf), 20, 5, dev, world)
+        tl["allreduce_us"] = ms_ar / 20 * 1e3
+        tl["allreduce_bytes"] = int(buf.numel() * 4)
+        tl["collective"] = "one NCCL all-reduce (sum) of the flat fp32 buffer [all gradients | sum CE, rows, correct, overflow flag]"
+        out[f"cfg5_er_n100_c32_dp{world}_train"] = tl
+        del a, b
+        # strong scaling: a fixed global batch of 512 cfg3 pairs (64-wide, regular-degree-like density) over N GPUs
+        per = 512 // world
+        m64 = build(64)
+        m64.set_precision(prec)
+        a, b = er_pairs_on_device(min(per, 64), 500, 0.2, 0.1, dev, 70 + rank)
+        reps = max(1, per // a.shape[0])
+
+        def strong():
+            with torch.no_grad():
+                for _ in range(reps):
+                    s = m64({"input": a}, {"input": b})
+            return s
+        ms, _ = _time_steps(strong, 2, 3, dev, world)
+        out["cfg3_strong_512_pairs"] = {"value": 512 * 2 / (ms / 1e3), "unit": "pairs/s", "ms_per_512_pairs": ms / 2,
+                                        "pairs_per_gpu": per, "dtype": dt, "inputs": "ER p=0.2 n=500 (same dense shapes as cfg3)"}
+    return out
+
+
 def cpu_reference_rate(cfg, steps, warmup, pairs_per_step=1):
     """The reference algorithm (oracle port, fp32 torch CPU, all host threads) on a bounded sample."""
     from oracle import fgnn_oracle as O
@@ -146,6 +296,7 @@ def main():
                     help="fp16 (default) is the 16-bit mode that meets the north_star 2e-2 embedding tolerance against the "
                          "reference at this shape (tests/test_gpu_tc.py); bf16 runs the same tcgen05 kind::f16 kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary lines (cfg1 / cfg2 / cfg4 / cfg5)")
     ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (profiling runs only)")
     ap.add_argument("--train", action="store_true",
                     help="time the data-parallel TRAINING step (fwd + bwd + flat all-reduce + Adam) in --precision "
@@ -321,6 +472,13 @@ def main():
         pipe["primed"] = False                       # the timed run starts with an exposed copy of its own first input
         ms_e2e = timed(step_e2e, args.steps)
 
+    secondary = None
+    if not args.no_secondary and args.workload == DEFAULT_WORKLOAD and args.pairs == 0:
+        del x1_d, x2_d, x1_bufs
+        pkg._lib.release_workspaces()
+        torch.cuda.empty_cache()
+        secondary = run_secondaries(pkg, dev, rank, world, args.precision)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -383,6 +541,8 @@ def main():
                 "pipeline": "H2D on a side stream: x2 under this step's first embedder pass, next step's x1 under the "
                             "second (double-buffered); the run's first step copies its own x1 exposed"},
     }
+    if secondary is not None:
+        line["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sec = cpu_reference_rate(cfg, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
