@@ -283,23 +283,25 @@ __global__ void finalize_coef_kernel(CoefArgs a, int total) {
 
 
 // =============================================================================================
-// K_A: fused conv chains on tensor cores, software-pipelined over kSlots tiles in flight.
+// K_A: fused conv chains on tensor cores: kSlots virtual tiles in flight, ONE epilogue group per TMEM slot.
 //   tile  = 128 consecutive physical pixels (layout C) of one graph, all channels; NMLP (1 or 2) MLPs
-//           consume the same staged input tile ("virtual tiles" v = tile * NMLP + m)
-//   layer1: D[128 px, COUT] = X[px, K1] * W1f[g][m]^T   A = TMA-staged smem (MN-major), B = smem (K-major)
+//           consume the same staged input tile ("virtual tiles" v = tile * NMLP + m, slot = v % kSlots)
+//   layer1: D[128 px, COUT] = X[px, K1] * W1f[g][m]^T   A = TMA-staged smem (MN-major), B = smem (K-major);
+//           with NMLP = 2 the two MLPs' folded weights sit back to back in shared memory and their accumulators in
+//           adjacent TMEM columns, so ONE N = 2 COUT MMA chain reads the staged tile once for both
 //   layer>=2: D = relu(D + b) (16-bit, written back to TMEM) * W^T        A = TMEM, B = smem
 //   output: raw last-layer accumulators as 16-bit planes (the last bias cancels in GraphNorm): staged in shared
-//           memory with stmatrix.trans (16x256b accumulator fragments), stored by TMA; their per-(graph, channel)
-//           sum and sum of squares are taken from the staged tile by the statistics warps (fp32 partials per
-//           thread, double atomics on a graph change).  POOL = true (last block): the tile is not stored, the
-//           statistics warps also publish the row-wise max / min for the fused column-max pooling.
-// Warp roles (kWEpi / kWProd / kWMma / kWStat): warps 0-3 / 4-7 two epilogue groups, warp 8 TMA producer,
-// warps 9-10 MMA issuers (one per group), warps 11-14 GraphNorm statistics + TMA store; the groups alternate
-// virtual tiles (slot parity).  TMEM slot s: accumulator columns [s*1.5*COUT, +COUT), packed hidden activations
-// in the next COUT/2 columns.
-// Barrier rule: a waiter sees ONE parity bit of an mbarrier, so no waiter may skip a phase.  With NMLP = 1 the
-// two MMA warps consume alternate tiles of the input ring; each also observes the other's tile and releases its
-// stage (in_empty counts two arrivals).
+//           memory with stmatrix.trans (16x256b accumulator fragments), stored by TMA; per-(graph, channel) sum and
+//           sum of squares are taken from the staged tile by the group that produced it (fp32 partials per thread,
+//           double atomics on a graph change).  POOL = true (last block): the tile is not stored, the same pass
+//           also publishes the row-wise max / min for the fused column-max pooling.
+// Warp roles: warps 0-15 = four epilogue groups (group = warp / 4 = TMEM slot, lane quadrant = warp % 4), warp 16 = TMA
+// producer, warp 17 = first-layer MMA issuer (the only consumer of the input ring: it sees every phase of every
+// barrier it waits on).  The hidden layers' MMAs are issued by the group itself: after its pass the four warps meet
+// on a named barrier and one elected thread issues the next layer -- no hand-off to another warp sits on a slot's
+// chain accumulator -> tcgen05.ld -> bias/ReLU/pack -> tcgen05.st -> MMA, and the four chains are independent.
+// TMEM: accumulator of slot s in columns [s COUT, +COUT), its packed hidden activations in
+// [kSlots COUT + s COUT/2, +COUT/2).
 // =============================================================================================
 enum OutMode { kOutC = 0, kOutA = 1, kOutB = 2 };   // output plane layout: rows i / i + i/127 / i + i/(BN-1)
 
@@ -315,29 +317,17 @@ struct MlpArgs {
   int out_mode[2];                           // kOutC / kOutA / kOutB
   int ones[2];                               // kOutA: write the ones rows; kOutB: holes hold ones
   double* stat_acc;                          // [G][NMLP][COUT][2]
-  // Fused column-max pooling (last block): when rowenc[m] is set, MLP m's tile is NOT stored; the statistics warps
-  // fold the row-wise max and min of its valid pixels into rowenc[m][g][c][i][2] (order-preserving unsigned codes
+  // Fused column-max pooling (last block): when rowenc[m] is set, MLP m's tile is NOT stored; the statistics pass
+  // folds the row-wise max and min of its valid pixels into rowenc[m][g][c][i][2] (order-preserving unsigned codes
   // of max(y) and max(-y), buffer zeroed by the caller) and pool_finalize_kernel applies the GraphNorm affine.
   unsigned int* rowenc[2];
   const int32_t* n_per_graph;
 };
 
-constexpr int kSlots = 4;
-// warp roles of the conv-chain CTA (15 warps).  The scheduler prefers higher warp ids: the control warps sit on top so
-// that a wake-up is served at once (epilogue warps on top instead was measured 0.8% slower).
-constexpr int kWEpi = 0, kWProd = 8, kWMma = 9, kWStat = 11;
+constexpr int kSlots = 4;                    // TMEM slots = epilogue groups
+constexpr int kWProd = 4 * kSlots, kWL1 = kWProd + 1;
+constexpr int kMlpThreads = (kWL1 + 1) * 32;   // 576 -> 112 registers per thread
 
-// Optional cycle accounting of the conv-chain kernel's roles (compile with -DFGNN_TC_TIMING; bring-up only).
-#ifdef FGNN_TC_TIMING
-__device__ unsigned long long g_tc_timing[24];
-#define TIMING_DECL long long tm_t0 = clock64(), tm_acc[6] = {0, 0, 0, 0, 0, 0}
-#define TIMING_MARK(slot) do { long long tm_t1 = clock64(); tm_acc[slot] += tm_t1 - tm_t0; tm_t0 = tm_t1; } while (0)
-#define TIMING_FLUSH(base, cond) do { if (cond) for (int tm_i = 0; tm_i < 6; ++tm_i) atomicAdd(&g_tc_timing[(base) + tm_i], (unsigned long long)tm_acc[tm_i]); } while (0)
-#else
-#define TIMING_DECL
-#define TIMING_MARK(slot)
-#define TIMING_FLUSH(base, cond)
-#endif
 constexpr int kMaxInStages = 4;
 __host__ __device__ inline int mlp_in_stages(int K1) { return K1 >= 128 ? 3 : 4; }   // 32 KB stages at K1 = 128
 
@@ -350,18 +340,19 @@ template <int COUT, int NMLP>
 struct MlpSmem {
   static size_t bytes(int K1, int K1g, int depth, int Kh) {
     return 1024 + (size_t)mlp_in_stages(K1) * K1 * 256 + (size_t)2 * NMLP * K1g * COUT * 2 +
-           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)4 * COUT * 256 + mlp_bias_floats(COUT, NMLP, depth) * 4 + 512;
+           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)kSlots * COUT * 256 + mlp_bias_floats(COUT, NMLP, depth) * 4 + 512;
   }
 };
 
 template <typename T, int COUT, int NMLP, bool POOL, bool RELU_OUT>
-__global__ void __launch_bounds__(480, 1)
+__global__ void __launch_bounds__(kMlpThreads, 1)
 tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
               const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wh,
               const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
               const MlpArgs<T> args) {
-  constexpr int kSlotW = COUT * 3 / 2;
-  constexpr uint32_t kTmemCols = (kSlots * kSlotW <= 256) ? 256 : 512;
+  static_assert(kSlots % NMLP == 0, "a slot serves one MLP");
+  constexpr uint32_t kAccCols = kSlots * COUT, kHidCols = kSlots * COUT / 2;
+  constexpr uint32_t kTmemCols = (kAccCols + kHidCols <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   // round the base up to 1024 bytes with POINTER arithmetic: an integer round trip makes the compiler treat everything
   // behind it as generic memory (LD.E / ST.E instead of LDS / STS)
@@ -376,22 +367,20 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   uint8_t* s_in = smem;
   uint8_t* s_w1 = s_in + (size_t)kInStages * stage_bytes;      // [2 buffers][NMLP][atoms][COUT][128B]
   uint8_t* s_wh = s_w1 + (size_t)2 * w1_buf_bytes;             // [NMLP][depth-1][atoms][COUT][128B]
-  uint8_t* s_out = s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes;   // [2 groups][2 buffers][2 halves][COUT][128 B] swizzled
+  uint8_t* s_out = s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes;   // [kSlots groups][2 halves][COUT][128 B] swizzled
   // Biases live in shared memory: with > 200 KB of it carved out the L1 holds next to nothing, and 16 global
   // loads per epilogue pass (uniform address, L2 latency) were costing more than the rest of the pass together.
-  float* s_bias1 = reinterpret_cast<float*>(s_out + (size_t)4 * COUT * 256);   // [kSlots][COUT] folded first-layer bias of the slot's graph
-  float* s_biash = s_bias1 + kSlots * COUT;                                    // [NMLP][depth-2][COUT] biases of layers 1 .. depth-2
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + (size_t)4 * COUT * 256 + mlp_bias_floats(COUT, NMLP, depth) * 4);
+  float* s_bias1 = reinterpret_cast<float*>(s_out + (size_t)kSlots * COUT * 256);   // [kSlots][COUT] folded first-layer bias of the slot's graph
+  float* s_biash = s_bias1 + kSlots * COUT;                                         // [NMLP][depth-2][COUT] biases of layers 1 .. depth-2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + (size_t)kSlots * COUT * 256 + mlp_bias_floats(COUT, NMLP, depth) * 4);
   uint64_t* in_full = bars;                      // [kInStages]
   uint64_t* in_empty = in_full + kMaxInStages;   // [kInStages]
   uint64_t* w1_full = in_empty + kMaxInStages;   // [2]
   uint64_t* w1_empty = w1_full + 2;           // [2]
   uint64_t* wh_full = w1_empty + 2;           // [1]
-  uint64_t* mma_done = wh_full + 1;           // [kSlots]
-  uint64_t* h_ready = mma_done + kSlots;      // [kSlots]
-  uint64_t* tile_full = h_ready + kSlots;     // [2 groups][2 buffers] output tile staged in smem
-  uint64_t* tile_empty = tile_full + 4;       // [2][2] statistics warps are done with it AND its TMA store has read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 4);
+  uint64_t* mma_done = wh_full + 1;           // [kSlots] the slot's accumulator holds the next layer's result
+  uint64_t* acc_free = mma_done + kSlots;     // [kSlots] the final pass has drained the slot's accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + kSlots);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
 
@@ -403,11 +392,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   const long V = (t_end - t_begin) * NMLP;  // virtual tiles of this CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kInStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 2); }   // both MMA warps release every stage
-    for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 2); }
+    for (int s = 0; s < kInStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
     mbar_init(wh_full, 1);
-    for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&h_ready[s], 4); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&tile_full[s], 4); mbar_init(&tile_empty[s], 4); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&acc_free[s], 4); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < NMLP * (depth - 2) * COUT; i += blockDim.x) {
@@ -440,9 +428,6 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     }
   };
 
-
-  // Warp ids: the scheduler favours higher warp ids, and the two control warps must never be starved by
-  // epilogue warps polling an mbarrier on the same sub-partition -> control warps get the highest ids.
   if (warp == kWProd) {
     if (V > 0) {
       // ================= TMA producer (whole warp, elected lane issues) =================
@@ -490,457 +475,387 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         }
       }
     }
-  } else if (warp == kWMma || warp == kWMma + 1) {
-    // ================= MMA issuers: one warp per epilogue group (whole warp, elected lane issues) =================
-    // Warp 9+e feeds the two TMEM slots of group e in that group's own item order, so a slow group never
-    // blocks the other one and each issuer handles half of the tcgen05 traffic.
-    const int eg = warp - kWMma;
+  } else if (warp == kWL1) {
+    // ================= first-layer MMA issuer (whole warp, elected lane issues) =================
+    // Consumes the input ring and the per-graph weight buffers in order; slot s of tile `seq` is (seq NMLP + m) % kSlots,
+    // so the slots come round robin.  With NMLP = 2 one chain of N = 2 COUT MMAs fills both MLPs' accumulators.
     if (V > 0) {
-    const uint32_t idesc1 = make_idesc(Elem<T>::kFmt, /*A MN-major*/ 1, /*B K-major*/ 0, kTileM, COUT);
-    const uint32_t idesc2 = make_idesc(Elem<T>::kFmt, 0, 0, kTileM, COUT);
-    const uint64_t a_d0 = smem_desc_sw128(smem_u32(s_in), (uint32_t)K1 * 128u, 1024u);   // MN-major activations
-    const uint64_t b_d0 = smem_desc_sw128(smem_u32(s_w1), 16u, 1024u);                   // K-major weights
-    const uint32_t a_desc_lo0 = (uint32_t)a_d0, a_desc_hi = (uint32_t)(a_d0 >> 32);
-    const uint32_t w1_desc_lo0 = (uint32_t)b_d0, b_desc_hi = (uint32_t)(b_d0 >> 32);
-    const uint32_t wh_desc_lo0 = (uint32_t)smem_desc_sw128(smem_u32(s_wh), 16u, 1024u);
-    Walker wi;                               // walker of the issue path (layer-1 issues run ahead of the epilogue)
-    walker_init(wi);
-    walker_seek(wi, t_begin);
-    const int g_first = wi.g;
-    int issue_gidx = 0;                      // graphs (relative to g_first) whose weight buffer this group has released
-    auto release_graphs_upto = [&](int gidx) {   // all MMAs of this group that read buffers of graphs < gidx were issued
-      for (; issue_gidx < gidx; ++issue_gidx) mma_commit_e(&w1_empty[issue_gidx & 1]);
-    };
-    auto issue_layer1 = [&](long v, int s) {     // first conv of virtual tile v into slot s
-      const long seq = v / NMLP;
-      const int m = (int)(v % NMLP);
-      const int st = (int)(seq % kInStages);
-      walker_seek(wi, t_begin + seq);
-      const int gidx = wi.g - g_first;
-      if (gidx > issue_gidx) release_graphs_upto(gidx);
-      const int wbuf = gidx & 1;
-      mbar_wait(&w1_full[wbuf], (uint32_t)(gidx >> 1) & 1u);
-      if constexpr (NMLP == 1) {
-        // With one MLP the two issuers consume ALTERNATE tiles of the input ring.  A waiter that skips phases of an
-        // mbarrier cannot tell phase k from phase k+2 (one parity bit), so this warp also observes the other
-        // group's tile seq-1 and releases its stage; in_empty therefore always counts two arrivals and a stage
-        // cannot be refilled before both issuers have seen its current contents' phase.
-        if (seq > 0) {
-          const long q = seq - 1;
-          const int sq = (int)(q % kInStages);
-          mbar_wait(&in_full[sq], (uint32_t)(q / kInStages) & 1u);
-          if (lane == 0) mbar_arrive(&in_empty[sq]);
-          __syncwarp();
-        }
-      }
-      mbar_wait(&in_full[st], (uint32_t)(seq / kInStages) & 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
-      uint32_t a_lo = a_desc_lo0 + (uint32_t)st * (stage_bytes >> 4);
-      uint32_t b_lo = w1_desc_lo0 + (((uint32_t)wbuf * w1_buf_bytes + (uint32_t)m * w1_mlp_bytes) >> 4);
-      if (elect_one_sync()) {
-        const int ksteps = K1 / 16;
-#pragma unroll 1
-        for (int k = 0; k < ksteps; ++k) {
-          mma_ss2(d_tmem, a_lo, a_desc_hi, b_lo, b_desc_hi, idesc1, k > 0 ? 1u : 0u);
-          a_lo += 2048u >> 4;                                       // next 16 K-rows of the MN-major tile
-          b_lo += ((k & 3) == 3) ? ((COUT * 128u - 96u) >> 4) : (32u >> 4);  // next K atom / next 32 B
-        }
-        mma_commit(&in_empty[st]);             // NMLP arrivals free the input stage
-        mma_commit(&mma_done[s]);
-      }
-      __syncwarp();
-    };
-    auto issue_hidden = [&](int s, int m, int l) {   // layer l >= 1 of the tile in slot s: A = packed activations in TMEM
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(s * kSlotW);
-      const uint32_t wl_lo = wh_desc_lo0 + (uint32_t)(m * (depth - 1) + (l - 1)) * (wh_mat_bytes >> 4);
-      if (elect_one_sync()) {
+      constexpr bool kMerge = (NMLP == 2);          // the two folded weight matrices are contiguous only with ONE K atom
+      const bool merge = kMerge && K1g == 64;
+      const uint32_t idesc1 = make_idesc(Elem<T>::kFmt, /*A MN-major*/ 1, /*B K-major*/ 0, kTileM, COUT);
+      const uint32_t idesc1w = make_idesc(Elem<T>::kFmt, 1, 0, kTileM, 2 * COUT);
+      const uint64_t a_d0 = smem_desc_sw128(smem_u32(s_in), (uint32_t)K1 * 128u, 1024u);   // MN-major activations
+      const uint64_t b_d0 = smem_desc_sw128(smem_u32(s_w1), 16u, 1024u);                   // K-major weights
+      const uint32_t a_desc_lo0 = (uint32_t)a_d0, a_desc_hi = (uint32_t)(a_d0 >> 32);
+      const uint32_t w1_desc_lo0 = (uint32_t)b_d0, b_desc_hi = (uint32_t)(b_d0 >> 32);
+      Walker wi;
+      walker_init(wi);
+      walker_seek(wi, t_begin);
+      const int g_first = wi.g;
+      int issue_gidx = 0;                      // graphs (relative to g_first) whose weight buffer has been released
+      uint32_t ph_free = 0;                    // phase bits of acc_free[s]
+      const long ntiles = t_end - t_begin;
+      for (long seq = 0; seq < ntiles; ++seq) {
+        const int st = (int)(seq % kInStages);
+        walker_seek(wi, t_begin + seq);
+        const int gidx = wi.g - g_first;
+        for (; issue_gidx < gidx; ++issue_gidx) mma_commit_e(&w1_empty[issue_gidx & 1]);   // every MMA that read it was issued
+        const int wbuf = gidx & 1;
+        mbar_wait(&w1_full[wbuf], (uint32_t)(gidx >> 1) & 1u);
+        mbar_wait(&in_full[st], (uint32_t)(seq / kInStages) & 1u);
+        const int s0 = (int)((seq * NMLP) % kSlots);
 #pragma unroll
-        for (int k = 0; k < COUT / 16; ++k)
-          mma_ts2(d_tmem, d_tmem + COUT + (uint32_t)k * 8u,
-                  wl_lo + (((uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u) >> 4), b_desc_hi, idesc2,
-                  k > 0 ? 1u : 0u);
-        mma_commit(&mma_done[s]);
-      }
-      __syncwarp();
-    };
-      if (depth > 1) mbar_wait(wh_full, 0);
-      for (int s = eg; s < kSlots; s += 2)     // prime both slots with the first wave
-        if (s < V) issue_layer1(s, s);
-      uint32_t ph_h = 0;                       // phase bits of h_ready[s]
-      TIMING_DECL;
-      for (long v0 = 0; v0 < V; v0 += kSlots) {
+        for (int m = 0; m < NMLP; ++m) {
+          if (seq * NMLP + m >= kSlots) { mbar_wait(&acc_free[s0 + m], (ph_free >> (s0 + m)) & 1u); ph_free ^= 1u << (s0 + m); }
+        }
+        tc_fence_after();
+        const uint32_t a_lo0 = a_desc_lo0 + (uint32_t)st * (stage_bytes >> 4);
+        const uint32_t b_lo0 = w1_desc_lo0 + (((uint32_t)wbuf * w1_buf_bytes) >> 4);
+        if (elect_one_sync()) {
+          const int ksteps = K1 / 16;
+          if (merge) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(s0 * COUT);
+            uint32_t a_lo = a_lo0, b_lo = b_lo0;
 #pragma unroll 1
-        for (int l = 0; l < depth; ++l) {
+            for (int k = 0; k < ksteps; ++k) {
+              mma_ss2(d_tmem, a_lo, a_desc_hi, b_lo, b_desc_hi, idesc1w, k > 0 ? 1u : 0u);
+              a_lo += 2048u >> 4;                                       // next 16 K-rows of the MN-major tile
+              b_lo += 32u >> 4;                                         // next 32 B of the single K atom
+            }
+          } else {
 #pragma unroll 1
-          for (int s = eg; s < kSlots; s += 2) {
-            const long v = v0 + s;
-            if (v >= V) break;
-            const int m = (int)(v % NMLP);
-            TIMING_MARK(0);
-            mbar_wait(&h_ready[s], (ph_h >> s) & 1u);   // epilogue of (v, l) done: operand written / accumulator drained
-            ph_h ^= 1u << s;
-            TIMING_MARK(2);
-            if (l < depth - 1) { issue_hidden(s, m, l + 1); TIMING_MARK(4); }
-            else if (v + kSlots < V) { issue_layer1(v + kSlots, s); TIMING_MARK(3); }
+            for (int m = 0; m < NMLP; ++m) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((s0 + m) * COUT);
+              uint32_t a_lo = a_lo0, b_lo = b_lo0 + (((uint32_t)m * w1_mlp_bytes) >> 4);
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k) {
+                mma_ss2(d_tmem, a_lo, a_desc_hi, b_lo, b_desc_hi, idesc1, k > 0 ? 1u : 0u);
+                a_lo += 2048u >> 4;
+                b_lo += ((k & 3) == 3) ? ((COUT * 128u - 96u) >> 4) : (32u >> 4);  // next K atom / next 32 B
+              }
+            }
           }
-        }
-      }
-      TIMING_FLUSH(0, warp == kWMma && lane == 0);
-      Walker wl = wi;                          // the producer may still wait for this group's release of later graphs
-      walker_seek(wl, t_end - 1);
-      release_graphs_upto(wl.g - g_first + 1);
-    }
-  } else if (warp >= kWStat && warp < kWStat + 4) {
-    // ================= statistics warps (kWStat .. +3): sum / sum of squares per channel from the staged tile ======
-    // thread -> (channel c, part): `part` selects a run of kPxPerPart consecutive pixels of the 128-pixel tile
-    constexpr int kParts = 128 / COUT;             // 2 for COUT = 64, 4 for COUT = 32
-    constexpr int kPxPerPart = 128 / kParts;       // 64 / 32 pixels = 8 / 4 16-byte chunks of one 64-pixel half
-    const int st = threadIdx.x - kWStat * 32;              // 0..127
-    const int c = st % COUT, part = st / COUT;
-    const int half = (part * kPxPerPart) / 64, chunk0 = ((part * kPxPerPart) % 64) / 8;
-    float acc_s[NMLP], acc_q[NMLP];
-    int acc_g[NMLP];
+          mma_commit(&in_empty[st]);
 #pragma unroll
-    for (int m = 0; m < NMLP; ++m) { acc_s[m] = 0.f; acc_q[m] = 0.f; acc_g[m] = -1; }
-    auto flush = [&](int m) {
-      if (acc_g[m] < 0) return;
-      double* dst = args.stat_acc + (((long)acc_g[m] * NMLP + m) * COUT + c) * 2;
-      atomicAdd(dst, (double)acc_s[m]);
-      atomicAdd(dst + 1, (double)acc_q[m]);
-      acc_s[m] = 0.f;
-      acc_q[m] = 0.f;
-    };
+          for (int m = 0; m < NMLP; ++m) mma_commit(&mma_done[s0 + m]);
+        }
+        __syncwarp();
+      }
+      Walker wl = wi;                          // the producer may still wait for the release of later graphs
+      walker_seek(wl, t_end - 1);
+      for (; issue_gidx < wl.g - g_first + 1; ++issue_gidx) mma_commit_e(&w1_empty[issue_gidx & 1]);
+    }
+  } else {
+    // ================= epilogue groups (warps 4s .. 4s+3 own TMEM slot s) =================
+    const int s = warp >> 2;                 // group = slot
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int et = threadIdx.x - s * 128;    // thread index inside the group = pixel of the tile
+    const int m = s % NMLP;                  // the MLP this slot serves
+    const int bar_id = 1 + s;
+    const uint32_t acc_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * COUT);
+    const uint32_t hid_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + kAccCols + (uint32_t)(s * (COUT / 2));
+    uint8_t* tile = s_out + (size_t)s * (COUT * 256);      // [half][COUT rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+    const bool storer = !POOL && lane == 0 && quad < 2;    // lane 0 of the group's first two warps: one 64-pixel half each
+    const uint32_t idesc2 = make_idesc(Elem<T>::kFmt, 0, 0, kTileM, COUT);
+    const uint32_t wh_desc_lo0 = (uint32_t)smem_desc_sw128(smem_u32(s_wh), 16u, 1024u);
+    const uint32_t wh_desc_hi = (uint32_t)(smem_desc_sw128(smem_u32(s_wh), 16u, 1024u) >> 32);
+    uint32_t ph_mma = 0;                     // parity of mma_done[s]
+    bool wh_ready = false;
     Walker w;
     walker_init(w);
-    int items[2] = {0, 0};                         // final items consumed per epilogue group
-    // fused pooling: running max / min of this thread's channel over the row it is currently in (consecutive tiles
-    // of a CTA are consecutive pixels, so a row spans several of them) -> one pair of atomics per row, not per tile
+    int bias_g = -1;                         // graph whose folded first-layer bias sits in s_bias1[s]
+
+    // ---- statistics state: thread -> (channel c, part): `part` selects a run of kPxPerPart consecutive pixels ----
+    constexpr int kParts = 128 / COUT;             // 2 for COUT = 64, 4 for COUT = 32
+    constexpr int kPxPerPart = 128 / kParts;       // 64 / 32 pixels = 8 / 4 16-byte chunks of one 64-pixel half
+    const int c = et % COUT, part = et / COUT;
+    const int half = (part * kPxPerPart) / 64, chunk0 = ((part * kPxPerPart) % 64) / 8;
+    float acc_s = 0.f, acc_q = 0.f;
+    int acc_g = -1;
+    auto flush = [&]() {
+      if (acc_g < 0) return;
+      double* dst = args.stat_acc + (((long)acc_g * NMLP + m) * COUT + c) * 2;
+      atomicAdd(dst, (double)acc_s);
+      atomicAdd(dst + 1, (double)acc_q);
+      acc_s = 0.f;
+      acc_q = 0.f;
+    };
+    // fused pooling: running max / min of this thread's channel over the row it is currently in -> one pair of
+    // atomics per (row, run of tiles this group sees in it)
     float pool_mx = -INFINITY, pool_mn = INFINITY;
-    int pool_row = -1, pool_g = -1, pool_m = 0;
+    int pool_row = -1, pool_g = -1;
     auto pool_flush = [&]() {
       if (pool_row >= 0 && pool_mx >= pool_mn) {
-        unsigned int* dst = args.rowenc[pool_m] + ((((long)pool_g * COUT + c) * geo.N + pool_row) << 1);
+        unsigned int* dst = args.rowenc[m] + ((((long)pool_g * COUT + c) * geo.N + pool_row) << 1);
         atomicMax(dst, enc_ordered(pool_mx));
         atomicMax(dst + 1, enc_ordered(-pool_mn));
       }
       pool_mx = -INFINITY;
       pool_mn = INFINITY;
     };
-    TIMING_DECL;
-    for (long v = 0; v < V; ++v) {
-      TIMING_MARK(0);
-      const int b = (int)(v & 1);                  // epilogue group (= slot parity) that produced this tile
-      const int kb = (b == 0) ? items[0]++ : items[1]++;
-      const int buf = b * 2 + (kb & 1);
-      const int m = (int)(v % NMLP);
-      walker_seek(w, t_begin + v / NMLP);
-      const int g = w.g;
-      const int p0 = (int)(t_begin + v / NMLP - w.base) * kTileM;
+
+    for (long v = s; v < V; v += kSlots) {
+      const long seq = v / NMLP;
+      walker_seek(w, t_begin + seq);
+      const int g = w.g, n = w.n;
+      if ((depth > 1 || RELU_OUT) && g != bias_g) {
+        // first tile of a new graph in this slot.  Every warp of the group has passed a named barrier since it last
+        // read s_bias1 (the barrier that ends the pass), so the vector may be overwritten.
+        if (et < COUT) s_bias1[s * COUT + et] = __ldg(args.bias1 + ((long)g * NMLP + m) * COUT + et);
+        named_bar_sync(bar_id, 128);
+        bias_g = g;
+      }
+#pragma unroll 1
+      for (int l = 0; l < depth - 1; ++l) {
+        // ---------------- hidden pass: accumulator -> relu(acc + b) as the next layer's 16-bit A operand in TMEM ----------------
+        mbar_wait(&mma_done[s], ph_mma);
+        ph_mma ^= 1u;
+        tc_fence_after();
+        const float* bias = (l == 0) ? (s_bias1 + s * COUT) : (s_biash + (m * (depth - 2) + (l - 1)) * COUT);
+        {
+          // all accumulator columns in flight at once: one TMEM round trip per item instead of one per 32 columns;
+          // the biases of the first 32 columns are fetched from shared memory while that load is in flight
+          const uint32_t bias_s = smem_u32(bias);
+          uint32_t r[COUT];
 #pragma unroll
-      for (int mm = 0; mm < NMLP; ++mm)
-        if (mm == m && g != acc_g[mm]) { flush(mm); acc_g[mm] = g; }
-      TIMING_MARK(1);
-      mbar_wait(&tile_full[buf], (uint32_t)(kb >> 1) & 1u);
-      TIMING_MARK(2);
-      constexpr bool pooled = POOL;                      // compile-time: the non-pooled kernels carry none of this
-      const bool storer = !pooled && lane == 0 && warp < kWStat + 2;   // lane 0 of the first two statistics warps: one half each
+          for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld32(acc_addr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
+#pragma unroll
+          for (int c0 = 0; c0 < COUT; c0 += 32) {
+            float4 bq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) bq[u] = lds128(bias_s + (uint32_t)(c0 + 4 * u) * 4u);
+            if (c0 == 0) tmem_wait_ld();
+            uint32_t h[16];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              float x0 = __uint_as_float(r[c0 + 4 * u]), x1 = __uint_as_float(r[c0 + 4 * u + 1]);
+              float x2 = __uint_as_float(r[c0 + 4 * u + 2]), x3 = __uint_as_float(r[c0 + 4 * u + 3]);
+              add2(x0, x1, bq[u].x, bq[u].y);
+              add2(x2, x3, bq[u].z, bq[u].w);
+              h[2 * u] = Elem<T>::pack_relu(x0, x1);
+              h[2 * u + 1] = Elem<T>::pack_relu(x2, x3);
+            }
+            tmem_st16(hid_addr + (uint32_t)(c0 / 2), h);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        // the staging buffer must be free before the final pass: the store of this group's previous tile has read it
+        if (l == depth - 2 && storer) bulk_wait_group_read0();
+        named_bar_sync(bar_id, 128);           // all four quadrants of the operand are written (and fenced)
+        if (quad == 0) {
+          // this group issues its own next layer: A = packed activations in TMEM, B = the layer's weights in smem
+          if (!wh_ready) { mbar_wait(wh_full, 0); wh_ready = true; }
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(s * COUT);
+          const uint32_t a_tmem = tmem_base + kAccCols + (uint32_t)(s * (COUT / 2));
+          const uint32_t wl_lo = wh_desc_lo0 + (uint32_t)(m * (depth - 1) + l) * (wh_mat_bytes >> 4);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < COUT / 16; ++k)
+              mma_ts2(d_tmem, a_tmem + (uint32_t)k * 8u,
+                      wl_lo + (((uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u) >> 4), wh_desc_hi, idesc2,
+                      k > 0 ? 1u : 0u);
+            mma_commit(&mma_done[s]);
+          }
+          __syncwarp();
+        }
+      }
+      // ---------------- final pass: raw accumulator -> staged 16-bit tile -> TMA store + statistics ----------------
+      if (depth == 1) {                        // (with hidden layers the last hidden pass's barrier covers this)
+        if (storer) bulk_wait_group_read0();
+        named_bar_sync(bar_id, 128);           // staging buffer free: its store and every thread's statistics pass are done
+      }
+      mbar_wait(&mma_done[s], ph_mma);
+      ph_mma ^= 1u;
+      tc_fence_after();
+      // pixel coordinates with 32-bit arithmetic: one division per tile, then at most two row wraps
+      const int p0 = (int)(t_begin + seq - w.base) * kTileM;
+      int pi = p0 / geo.NPC;
+      int pj = p0 - pi * geo.NPC + et;
+      if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
+      if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
+      const bool in_plane = pi < geo.N;
+      const bool hole = (pj & (geo.BN - 1)) == geo.BN - 1;
+      const int j = pj - (pj >> geo.BNLOG);
+      const bool valid = in_plane && !hole && pi < n && j < n;
+      const int mode = args.out_mode[m];
+      // holes of Y2 (layout B) hold ones on valid rows: they are the matmul's ones column
+      const float marker = (hole && mode == kOutB && args.ones[m] && pi < n) ? 1.f : 0.f;
+      {
+        // Transposing store: the 16x256b TMEM load hands every thread channel PAIRS of four pixels (the mma
+        // C-fragment layout), one packed convert per pair, and stmatrix.trans writes 8 channels x 8 pixels as
+        // eight 16-byte row pieces -> 8 stmatrix per warp instead of 64 two-byte stores per thread.
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t mmask = __ballot_sync(0xffffffffu, marker != 0.f);
+        uint32_t rl[COUT / 2], ru[COUT / 2];
+        if constexpr (COUT == 64) {
+          tmem_ld_16x256b_x8(acc_addr, rl);
+          tmem_ld_16x256b_x8(acc_addr + (16u << 16), ru);
+        } else {
+          tmem_ld_16x256b_x4(acc_addr, rl);
+          tmem_ld_16x256b_x4(acc_addr + (16u << 16), ru);
+        }
+        const int q4 = lane >> 2;
+        const uint32_t one2 = Elem<T>::pack(1.f, 1.f);
+        bool vb[4];
+        uint32_t fill[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vb[i] = (vmask >> (8 * i + q4)) & 1u;
+          fill[i] = ((mmask >> (8 * i + q4)) & 1u) ? one2 : 0u;
+        }
+        // this thread supplies the address of row (lane % 8) of matrix (lane / 8): channel 8u + lane % 8,
+        // pixels quad * 32 + 8 * (lane / 8) .. + 7 = 16-byte chunk (quad & 1) * 4 + lane / 8 of half quad / 2
+        const uint32_t st_addr = smem_u32(tile) + (uint32_t)(quad >> 1) * (COUT * 128) + (uint32_t)(lane & 7) * 128 +
+                                 (uint32_t)(((((quad & 1) << 2) + (lane >> 3)) ^ (lane & 7)) << 4);
+        tmem_wait_ld();
+        tc_fence_before();                 // accumulator drained: the slot may take its next tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_free[s]);
+        if constexpr (RELU_OUT) {
+          // training forward, every conv layer is its own depth-1 launch: out = relu(acc + bias), bias of this
+          // thread's channel pair 8u + 2 * (lane % 4), +1 from the slot's folded first-layer bias
+          const float* bsl = s_bias1 + s * COUT + 2 * (lane & 3);     // RELU_OUT launches have depth == 1
+#pragma unroll
+          for (int u = 0; u < COUT / 8; ++u) {
+            const float2 bb = *reinterpret_cast<const float2*>(bsl + 8 * u);
+            rl[4 * u] = __float_as_uint(__uint_as_float(rl[4 * u]) + bb.x);
+            rl[4 * u + 1] = __float_as_uint(__uint_as_float(rl[4 * u + 1]) + bb.y);
+            rl[4 * u + 2] = __float_as_uint(__uint_as_float(rl[4 * u + 2]) + bb.x);
+            rl[4 * u + 3] = __float_as_uint(__uint_as_float(rl[4 * u + 3]) + bb.y);
+            ru[4 * u] = __float_as_uint(__uint_as_float(ru[4 * u]) + bb.x);
+            ru[4 * u + 1] = __float_as_uint(__uint_as_float(ru[4 * u + 1]) + bb.y);
+            ru[4 * u + 2] = __float_as_uint(__uint_as_float(ru[4 * u + 2]) + bb.x);
+            ru[4 * u + 3] = __float_as_uint(__uint_as_float(ru[4 * u + 3]) + bb.y);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < COUT / 8; ++u) {
+          if constexpr (RELU_OUT) {
+            const uint32_t w0 = vb[0] ? Elem<T>::pack_relu(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
+            const uint32_t w1 = vb[1] ? Elem<T>::pack_relu(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
+            const uint32_t w2 = vb[2] ? Elem<T>::pack_relu(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
+            const uint32_t w3 = vb[3] ? Elem<T>::pack_relu(__uint_as_float(ru[4 * u + 2]), __uint_as_float(ru[4 * u + 3])) : fill[3];
+            stmatrix_x4_trans(st_addr + (uint32_t)u * 1024u, w0, w1, w2, w3);
+            continue;
+          }
+          const uint32_t w0 = vb[0] ? Elem<T>::pack(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
+          const uint32_t w1 = vb[1] ? Elem<T>::pack(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
+          const uint32_t w2 = vb[2] ? Elem<T>::pack(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
+          const uint32_t w3 = vb[3] ? Elem<T>::pack(__uint_as_float(ru[4 * u + 2]), __uint_as_float(ru[4 * u + 3])) : fill[3];
+          stmatrix_x4_trans(st_addr + (uint32_t)u * 1024u, w0, w1, w2, w3);
+        }
+      }
+      fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
+      named_bar_sync(bar_id, 128);         // the tile is staged
       if (storer) {
-        // the four epilogue warps have staged the tile and fenced it for the async proxy: store it (one 64-pixel
-        // half per TMA; a half never straddles a row because NPC % 64 == 0)
+        // store it: one 64-pixel half per TMA (a half never straddles a row because NPC % 64 == 0)
         const CUtensorMap* mo = (m == 0) ? &map_o0 : &map_o1;
-        const int mode = args.out_mode[m];
-        const int hf = warp - kWStat;
-        const int ph = p0 + hf * 64;
+        const int ph = p0 + quad * 64;
         const int prw = ph / geo.NPC, col = ph - prw * geo.NPC;
         const int prow = (mode == kOutA) ? prw + prw / kTM1 : (mode == kOutB ? prw + prw / geo.TN1 : prw);
-        if (prw < geo.N) tma_store_3d(mo, s_out + (size_t)buf * (COUT * 256) + (size_t)hf * (COUT * 128), col, prow, g * COUT);
+        if (prw < geo.N) tma_store_3d(mo, tile + (size_t)quad * (COUT * 128), col, prow, g * COUT);
         bulk_commit_group();
       }
-      const uint8_t* row = s_out + (size_t)buf * (COUT * 256) + (size_t)half * (COUT * 128) + (size_t)c * 128;
-      const uint32_t row_s = smem_u32(row);          // explicit shared-space loads: `smem` is a generic pointer to the compiler
-      float sv = 0.f, qv = 0.f;
-      // fused pooling (see below): position of this thread's run, and whether all of it lies inside the graph
-      const int pstart = p0 + part * kPxPerPart;
-      const int pool_pi = pstart / geo.NPC, pool_pj0 = pstart - pool_pi * geo.NPC;
-      const bool pool_in = pooled && pool_pi < w.n && pool_pi < geo.N;
-      const int pool_pj_end = phys_k_end(w.n, geo.TN1);
-      const bool pool_full = pool_in && pool_pj0 + kPxPerPart <= pool_pj_end;      // warp-uniform (part is per warp)
-      if (pooled && (pool_pi != pool_row || g != pool_g || m != pool_m)) {
-        pool_flush();
-        pool_row = pool_in ? pool_pi : -1;
-        pool_g = g;
-        pool_m = m;
-      }
-      if (!pool_full) {
-        float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;    // even / odd pixels, packed fp32x2 arithmetic
-#pragma unroll
-        for (int k = 0; k < kPxPerPart / 8; ++k) {
-          const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 f = Elem<T>::unpack2(ww[u]);
-            sum_sq2(sa, sb, qa, qb, f.x, f.y);
-          }
-        }
-        sv = sa + sb;
-        qv = qa + qb;
-      } else {
-        // same pass with the row max / min folded in.  A hole column can only be the LAST pixel of a run (runs start
-        // at multiples of kPxPerPart, BN is a multiple of 64): one guarded element, no per-pixel tests.
-        const bool last_hole = ((pool_pj0 + kPxPerPart - 1) & (geo.BN - 1)) == geo.BN - 1;
-        float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, mx = pool_mx, mn = pool_mn;
-#pragma unroll
-        for (int k = 0; k < kPxPerPart / 8; ++k) {
-          const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 f = Elem<T>::unpack2(ww[u]);
-            sum_sq2(sa, sb, qa, qb, f.x, f.y);
-            mx = fmaxf(mx, f.x);
-            mn = fminf(mn, f.x);
-            if (k < kPxPerPart / 8 - 1 || u < 3 || !last_hole) { mx = fmaxf(mx, f.y); mn = fminf(mn, f.y); }
-          }
-        }
-        sv = sa + sb;
-        qv = qa + qb;
-        pool_mx = mx;
-        pool_mn = mn;
-      }
-      // hole pixels hold a marker (0 or 1), not data: take them out again
-      for (int hp = (geo.BN - 1 - (p0 & (geo.BN - 1))) & (geo.BN - 1); hp < 128; hp += geo.BN) {
-        if (hp >= part * kPxPerPart && hp < (part + 1) * kPxPerPart) {
-          const uint8_t* hrow = s_out + (size_t)buf * (COUT * 256) + (size_t)(hp >> 6) * (COUT * 128) + (size_t)c * 128;
-          const uint16_t raw = *reinterpret_cast<const uint16_t*>(hrow + ((((hp & 63) >> 3) ^ (c & 7)) << 4) + (hp & 7) * 2);
-          const float x = Elem<T>::to_float(*reinterpret_cast<const T*>(&raw));
-          sv -= x;
-          qv -= x * x;
+      // ones rows of Y1 (layout A): the last logical row of every 127-row matmul tile writes the row below it
+      if (mode == kOutA && args.ones[m] && in_plane && pi < n) {
+        const int mt = pi / kTM1;
+        if (pi - mt * kTM1 == kTM1 - 1 || pi == n - 1) {
+          T* o1 = args.out[m] + (long)g * COUT * geo.PSA + (long)(mt * 128 + 127) * geo.NPC + pj;
+          const T ov = Elem<T>::from_float((!hole && j < n) ? 1.f : 0.f);
+          for (int cc = 0; cc < COUT; ++cc) o1[(long)cc * geo.PSA] = ov;
         }
       }
-#pragma unroll
-      for (int mm = 0; mm < NMLP; ++mm)
-        if (mm == m) { acc_s[mm] += sv; acc_q[mm] += qv; }
-      if (pool_in && !pool_full) {
-        // run that crosses the end of the graph's columns: per-pixel tests
-        float mx = pool_mx, mn = pool_mn;
-#pragma unroll 1
-        for (int k = 0; k < kPxPerPart / 8; ++k) {
-          const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 f = Elem<T>::unpack2(ww[u]);
-            const int pj = pool_pj0 + 8 * k + 2 * u;
-            if (pj < pool_pj_end && (pj & (geo.BN - 1)) != geo.BN - 1) { mx = fmaxf(mx, f.x); mn = fminf(mn, f.x); }
-            if (pj + 1 < pool_pj_end && ((pj + 1) & (geo.BN - 1)) != geo.BN - 1) { mx = fmaxf(mx, f.y); mn = fminf(mn, f.y); }
-          }
+      // ---------------- statistics of the staged tile: sum / sum of squares per channel (+ row max / min) ----------------
+      if (g != acc_g) { flush(); acc_g = g; }
+      {
+        const uint8_t* row = tile + (size_t)half * (COUT * 128) + (size_t)c * 128;
+        const uint32_t row_s = smem_u32(row);          // explicit shared-space loads
+        float sv = 0.f, qv = 0.f;
+        // fused pooling: position of this thread's run, and whether all of it lies inside the graph
+        const int pstart = p0 + part * kPxPerPart;
+        const int pool_pi = pstart / geo.NPC, pool_pj0 = pstart - pool_pi * geo.NPC;
+        const bool pool_in = POOL && pool_pi < n && pool_pi < geo.N;
+        const int pool_pj_end = phys_k_end(n, geo.TN1);
+        const bool pool_full = pool_in && pool_pj0 + kPxPerPart <= pool_pj_end;      // warp-uniform (part is per warp)
+        if (POOL && (pool_pi != pool_row || g != pool_g)) {
+          pool_flush();
+          pool_row = pool_in ? pool_pi : -1;
+          pool_g = g;
         }
-        pool_mx = mx;
-        pool_mn = mn;
-      }
-      TIMING_MARK(3);
-      if (storer) bulk_wait_group_read0();       // the store has read the staged tile (it ran under the statistics pass)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tile_empty[buf]);
-      TIMING_MARK(4);
-    }
-    if (pool_row >= 0) pool_flush();
-    TIMING_FLUSH(16, st == 0);
-    if (lane == 0 && warp < kWStat + 2) bulk_wait_group0();   // every store has landed before the CTA exits
+        if (!pool_full) {
+          float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;    // even / odd pixels, packed fp32x2 arithmetic
 #pragma unroll
-    for (int mm = 0; mm < NMLP; ++mm) flush(mm);
-  } else {
-    // ================= epilogue groups (warps 0-3 / 4-7) =================
-    // Each group owns two TMEM slots; its own MMA-issuing warp (9 + group) feeds them.
-    const int eg = (warp - kWEpi) / 4;                 // 0: slots 0,2   1: slots 1,3
-    const int quad = warp % 4;               // TMEM lane quadrant this warp may access
-    const int pix_in_tile = quad * 32 + lane;
-    uint32_t ph_mma = 0;                     // phase bits of mma_done[s]
-    int n_final = 0;                         // final-layer items this group has produced (staging buffer = n_final & 1)
-    Walker w;
-    walker_init(w);
-    const int et = threadIdx.x - kWEpi * 32 - eg * 128;   // thread index inside the group
-    int bias_g0 = -1, bias_g1 = -1;          // graph whose folded first-layer bias sits in s_bias1[slot]
-    int slot_g0 = 0, slot_g1 = 0, slot_n0 = 0, slot_n1 = 0;   // (graph, its n, first tile of graph) of the tile in this group's two slots
-    long slot_base0 = 0, slot_base1 = 0;
-    // staged output tiles of this group: 2 buffers x [half][COUT rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
-
-    TIMING_DECL;
-    for (long v0 = 0; v0 < V; v0 += kSlots) {
-#pragma unroll 1
-      for (int l = 0; l < depth; ++l) {
-#pragma unroll 1
-        for (int s = eg; s < kSlots; s += 2) {
-          const long v = v0 + s;
-          if (v >= V) break;
-          TIMING_MARK(0);
-          const long seq = v / NMLP;
-          const int m = (int)(v % NMLP);
-          const bool last = (l == depth - 1);
-          const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * kSlotW);
-          // the walker only moves forward: resolve (graph, first tile of graph) once per virtual tile, at
-          // layer 0, and remember it per slot for the later layers of the same tile
-          const bool second = s >= 2;
-          if (l == 0) {
-            walker_seek(w, t_begin + seq);
-            if (second) { slot_g1 = w.g; slot_n1 = w.n; slot_base1 = w.base; } else { slot_g0 = w.g; slot_n0 = w.n; slot_base0 = w.base; }
-          }
-          const int g = second ? slot_g1 : slot_g0;
-          const long gbase = second ? slot_base1 : slot_base0;
-          if (l == 0 && (depth > 1 || RELU_OUT) && g != (second ? bias_g1 : bias_g0)) {
-            // first tile of a new graph in this slot (m is fixed per slot: NMLP divides kSlots).  All four warps of the
-            // group take this branch at the same item, and the previous tile's layer-0 pass is long finished.
-            if (et < COUT) s_bias1[s * COUT + et] = __ldg(args.bias1 + ((long)g * NMLP + m) * COUT + et);
-            named_bar_sync(1 + eg, 128);
-            if (second) bias_g1 = g; else bias_g0 = g;
-          }
-          mbar_wait(&mma_done[s], (ph_mma >> s) & 1u);
-          ph_mma ^= 1u << s;
-          TIMING_MARK(1);
-          tc_fence_after();
-          if (!last) {
-            const float* bias = (l == 0) ? (s_bias1 + s * COUT) : (s_biash + (m * (depth - 2) + (l - 1)) * COUT);
-            {
-              // all accumulator columns in flight at once: one TMEM round trip per item instead of one per 32 columns;
-              // the biases of the first 32 columns are fetched from shared memory while that load is in flight, the
-              // others once the first half's registers are free (a single exposed LDS latency per pass)
-              const uint32_t bias_s = smem_u32(bias);
-              uint32_t r[COUT];
+          for (int k = 0; k < kPxPerPart / 8; ++k) {
+            const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-              for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld32(lane_addr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
-#pragma unroll
-              for (int c0 = 0; c0 < COUT; c0 += 32) {
-                float4 bq[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) bq[u] = lds128(bias_s + (uint32_t)(c0 + 4 * u) * 4u);
-                if (c0 == 0) tmem_wait_ld();
-                uint32_t h[16];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  float x0 = __uint_as_float(r[c0 + 4 * u]), x1 = __uint_as_float(r[c0 + 4 * u + 1]);
-                  float x2 = __uint_as_float(r[c0 + 4 * u + 2]), x3 = __uint_as_float(r[c0 + 4 * u + 3]);
-                  add2(x0, x1, bq[u].x, bq[u].y);
-                  add2(x2, x3, bq[u].z, bq[u].w);
-                  h[2 * u] = Elem<T>::pack_relu(x0, x1);
-                  h[2 * u + 1] = Elem<T>::pack_relu(x2, x3);
-                }
-                tmem_st16(lane_addr + (uint32_t)COUT + (uint32_t)(c0 / 2), h);
-              }
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = Elem<T>::unpack2(ww[u]);
+              sum_sq2(sa, sb, qa, qb, f.x, f.y);
             }
-            tmem_wait_st();
-            TIMING_MARK(2);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&h_ready[s]);   // next A operand complete (4 warps arrive)
-          } else {
-            const int n = second ? slot_n1 : slot_n0;
-            // pixel coordinates with 32-bit arithmetic: one division per tile, then at most two row wraps
-            const int p0 = (int)(t_begin + seq - gbase) * kTileM;
-            int pi = p0 / geo.NPC;
-            int pj = p0 - pi * geo.NPC + pix_in_tile;
-            if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
-            if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
-            const bool in_plane = pi < geo.N;
-            const bool hole = (pj & (geo.BN - 1)) == geo.BN - 1;
-            const int j = pj - (pj >> geo.BNLOG);
-            const bool valid = in_plane && !hole && pi < n && j < n;
-            const int mode = args.out_mode[m];
-            // holes of Y2 (layout B) hold ones on valid rows: they are the matmul's ones column
-            const float marker = (hole && mode == kOutB && args.ones[m] && pi < n) ? 1.f : 0.f;
-            // staging buffer: free once the statistics warps have read its previous tile and that tile's TMA store
-            // has read it too (thread 0 of the group arrives for the store, see below)
-            const int buf = eg * 2 + (n_final & 1);
-            uint8_t* tile = s_out + (size_t)buf * (COUT * 256);
-            mbar_wait(&tile_empty[buf], ((uint32_t)(n_final >> 1) & 1u) ^ 1u);
-            TIMING_MARK(3);
-            {
-              // Transposing store: the 16x256b TMEM load hands every thread channel PAIRS of four pixels (the mma
-              // C-fragment layout), one packed convert per pair, and stmatrix.trans writes 8 channels x 8 pixels as
-              // eight 16-byte row pieces -> 8 stmatrix per warp instead of 64 two-byte stores per thread.
-              const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-              const uint32_t mmask = __ballot_sync(0xffffffffu, marker != 0.f);
-              uint32_t rl[COUT / 2], ru[COUT / 2];
-              if constexpr (COUT == 64) {
-                tmem_ld_16x256b_x8(lane_addr, rl);
-                tmem_ld_16x256b_x8(lane_addr + (16u << 16), ru);
-              } else {
-                tmem_ld_16x256b_x4(lane_addr, rl);
-                tmem_ld_16x256b_x4(lane_addr + (16u << 16), ru);
-              }
-              const int q4 = lane >> 2;
-              const uint32_t one2 = Elem<T>::pack(1.f, 1.f);
-              bool vb[4];
-              uint32_t fill[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                vb[i] = (vmask >> (8 * i + q4)) & 1u;
-                fill[i] = ((mmask >> (8 * i + q4)) & 1u) ? one2 : 0u;
-              }
-              // this thread supplies the address of row (lane % 8) of matrix (lane / 8): channel 8u + lane % 8,
-              // pixels quad * 32 + 8 * (lane / 8) .. + 7 = 16-byte chunk (quad & 1) * 4 + lane / 8 of half quad / 2
-              const uint32_t st_addr = smem_u32(tile) + (uint32_t)(quad >> 1) * (COUT * 128) + (uint32_t)(lane & 7) * 128 +
-                                       (uint32_t)(((((quad & 1) << 2) + (lane >> 3)) ^ (lane & 7)) << 4);
-              tmem_wait_ld();
-              if constexpr (RELU_OUT) {
-                // training forward, every conv layer is its own depth-1 launch: out = relu(acc + bias), bias of this
-                // thread's channel pair 8u + 2 * (lane % 4), +1 from the slot's folded first-layer bias
-                const float* bsl = s_bias1 + s * COUT + 2 * (lane & 3);     // RELU_OUT launches have depth == 1
-#pragma unroll
-                for (int u = 0; u < COUT / 8; ++u) {
-                  const float2 bb = *reinterpret_cast<const float2*>(bsl + 8 * u);
-                  rl[4 * u] = __float_as_uint(__uint_as_float(rl[4 * u]) + bb.x);
-                  rl[4 * u + 1] = __float_as_uint(__uint_as_float(rl[4 * u + 1]) + bb.y);
-                  rl[4 * u + 2] = __float_as_uint(__uint_as_float(rl[4 * u + 2]) + bb.x);
-                  rl[4 * u + 3] = __float_as_uint(__uint_as_float(rl[4 * u + 3]) + bb.y);
-                  ru[4 * u] = __float_as_uint(__uint_as_float(ru[4 * u]) + bb.x);
-                  ru[4 * u + 1] = __float_as_uint(__uint_as_float(ru[4 * u + 1]) + bb.y);
-                  ru[4 * u + 2] = __float_as_uint(__uint_as_float(ru[4 * u + 2]) + bb.x);
-                  ru[4 * u + 3] = __float_as_uint(__uint_as_float(ru[4 * u + 3]) + bb.y);
-                }
-              }
-#pragma unroll
-              for (int u = 0; u < COUT / 8; ++u) {
-                if constexpr (RELU_OUT) {
-                  const uint32_t w0 = vb[0] ? Elem<T>::pack_relu(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
-                  const uint32_t w1 = vb[1] ? Elem<T>::pack_relu(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
-                  const uint32_t w2 = vb[2] ? Elem<T>::pack_relu(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
-                  const uint32_t w3 = vb[3] ? Elem<T>::pack_relu(__uint_as_float(ru[4 * u + 2]), __uint_as_float(ru[4 * u + 3])) : fill[3];
-                  stmatrix_x4_trans(st_addr + (uint32_t)u * 1024u, w0, w1, w2, w3);
-                  continue;
-                }
-                const uint32_t w0 = vb[0] ? Elem<T>::pack(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
-                const uint32_t w1 = vb[1] ? Elem<T>::pack(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
-                const uint32_t w2 = vb[2] ? Elem<T>::pack(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
-                const uint32_t w3 = vb[3] ? Elem<T>::pack(__uint_as_float(ru[4 * u + 2]), __uint_as_float(ru[4 * u + 3])) : fill[3];
-                stmatrix_x4_trans(st_addr + (uint32_t)u * 1024u, w0, w1, w2, w3);
-              }
-            }
-            TIMING_MARK(4);
-            tc_fence_before();                 // accumulator drained: the slot may take its next tile
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&h_ready[s]);
-            fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tile_full[buf]);   // 4 arrivals; the statistics warps store the tile and reduce it
-            ++n_final;
-            // ones rows of Y1 (layout A): the last logical row of every 127-row matmul tile writes the row below it
-            if (mode == kOutA && args.ones[m] && in_plane && pi < n) {
-              const int mt = pi / kTM1;
-              if (pi - mt * kTM1 == kTM1 - 1 || pi == n - 1) {
-                T* o1 = args.out[m] + (long)g * COUT * geo.PSA + (long)(mt * 128 + 127) * geo.NPC + pj;
-                const T ov = Elem<T>::from_float((!hole && j < n) ? 1.f : 0.f);
-                for (int c = 0; c < COUT; ++c) o1[(long)c * geo.PSA] = ov;
-              }
-            }
-            TIMING_MARK(5);
           }
+          sv = sa + sb;
+          qv = qa + qb;
+        } else {
+          // same pass with the row max / min folded in.  A hole column can only be the LAST pixel of a run (runs start
+          // at multiples of kPxPerPart, BN is a multiple of 64): one guarded element, no per-pixel tests.
+          const bool last_hole = ((pool_pj0 + kPxPerPart - 1) & (geo.BN - 1)) == geo.BN - 1;
+          float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f, mx = pool_mx, mn = pool_mn;
+#pragma unroll
+          for (int k = 0; k < kPxPerPart / 8; ++k) {
+            const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = Elem<T>::unpack2(ww[u]);
+              sum_sq2(sa, sb, qa, qb, f.x, f.y);
+              mx = fmaxf(mx, f.x);
+              mn = fminf(mn, f.x);
+              if (k < kPxPerPart / 8 - 1 || u < 3 || !last_hole) { mx = fmaxf(mx, f.y); mn = fminf(mn, f.y); }
+            }
+          }
+          sv = sa + sb;
+          qv = qa + qb;
+          pool_mx = mx;
+          pool_mn = mn;
+        }
+        // hole pixels hold a marker (0 or 1), not data: take them out again
+        for (int hp = (geo.BN - 1 - (p0 & (geo.BN - 1))) & (geo.BN - 1); hp < 128; hp += geo.BN) {
+          if (hp >= part * kPxPerPart && hp < (part + 1) * kPxPerPart) {
+            const uint8_t* hrow = tile + (size_t)(hp >> 6) * (COUT * 128) + (size_t)c * 128;
+            const uint16_t raw = *reinterpret_cast<const uint16_t*>(hrow + ((((hp & 63) >> 3) ^ (c & 7)) << 4) + (hp & 7) * 2);
+            const float x = Elem<T>::to_float(*reinterpret_cast<const T*>(&raw));
+            sv -= x;
+            qv -= x * x;
+          }
+        }
+        acc_s += sv;
+        acc_q += qv;
+        if (pool_in && !pool_full) {
+          // run that crosses the end of the graph's columns: per-pixel tests
+          float mx = pool_mx, mn = pool_mn;
+#pragma unroll 1
+          for (int k = 0; k < kPxPerPart / 8; ++k) {
+            const uint4 wv = lds128u(row_s + (uint32_t)(((chunk0 + k) ^ (c & 7)) << 4));
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = Elem<T>::unpack2(ww[u]);
+              const int pjx = pool_pj0 + 8 * k + 2 * u;
+              if (pjx < pool_pj_end && (pjx & (geo.BN - 1)) != geo.BN - 1) { mx = fmaxf(mx, f.x); mn = fminf(mn, f.x); }
+              if (pjx + 1 < pool_pj_end && ((pjx + 1) & (geo.BN - 1)) != geo.BN - 1) { mx = fmaxf(mx, f.y); mn = fminf(mn, f.y); }
+            }
+          }
+          pool_mx = mx;
+          pool_mn = mn;
         }
       }
     }
-    TIMING_FLUSH(8, warp == kWEpi + 2 && lane == 0);
+    if (POOL && pool_row >= 0) pool_flush();
+    if (storer) bulk_wait_group0();   // every store has landed before the CTA exits
+    flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -1388,11 +1303,11 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   if (grid < 1) grid = 1;
   prof::begin(prof::kMlp, st);
   if (pool) {
-    if constexpr (NMLP == 1) tc_mlp_kernel<T, COUT, NMLP, true, false><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+    if constexpr (NMLP == 1) tc_mlp_kernel<T, COUT, NMLP, true, false><<<grid, kMlpThreads, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
   } else if (L.relu_out) {
-    tc_mlp_kernel<T, COUT, NMLP, false, true><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+    tc_mlp_kernel<T, COUT, NMLP, false, true><<<grid, kMlpThreads, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
   } else {
-    tc_mlp_kernel<T, COUT, NMLP, false, false><<<grid, 480, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
+    tc_mlp_kernel<T, COUT, NMLP, false, false><<<grid, kMlpThreads, smem, st>>>(mx0, mx1, mw1, mwh, mo[0], mo[1], a);
   }
   prof::end(prof::kMlp, st);
   FGNN_LAUNCHED();
@@ -1829,27 +1744,6 @@ int debug_mlp(int precision, const fgnn_mlp_params& mp, const float* x, float* y
   return fail(FGNN_ERR_INVALID, "precision must be FGNN_BF16 or FGNN_FP16");
 }
 
-#ifdef FGNN_TC_TIMING
-void dump_timing() {
-  unsigned long long h[24];
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
-  const char* names[3][6] = {
-      {"loop/index", "-", "wait h_ready", "layer-1 issue (incl. input wait)", "hidden issue+commit", "-"},
-      {"loop/index", "wait mma_done", "hidden epilogue", "final: index + wait tile_empty", "final: tmem ld + cvt + stmatrix",
-       "final: fences + arrive"},
-      {"loop", "index + stat flush", "wait tile_full", "TMA store issue + reduce", "wait store read + arrive", "-"}};
-  const char* role[3] = {"MMA issuer (warp kWMma)", "epilogue warp 2", "first statistics thread"};
-  for (int r = 0; r < 3; ++r) {
-    unsigned long long tot = 0;
-    for (int i = 0; i < 6; ++i) tot += h[8 * r + i];
-    printf("%s (sum over CTAs, cycles):\n", role[r]);
-    for (int i = 0; i < 6; ++i) printf("  %-34s %14llu %5.1f%%\n", names[r][i], h[8 * r + i], 100.0 * h[8 * r + i] / (tot ? tot : 1));
-  }
-  unsigned long long z[24] = {0};
-  cudaMemcpyToSymbol(g_tc_timing, z, sizeof(z));
-}
-#else
 void dump_timing() {
 #ifdef FGNN_DEBUG_WAIT
   unsigned int h[4 + 128 * 4];
@@ -1864,7 +1758,6 @@ void dump_timing() {
   cudaMemcpyToSymbol(ptx::g_wait_dbg, z, sizeof(z));
 #endif
 }
-#endif
 
 }  // namespace tc
 }  // namespace fgnn
