@@ -160,6 +160,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same descriptor without swizzling (layout_type 0, "interleave"): 8-row x 16-byte core matrices stored contiguously
+// (128 B each); for a K-major operand LBO = byte distance between the two core matrices of one K = 16 step, SBO =
+// distance between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
 // Instruction descriptor for kind::f16 with fp32 accumulation.
 // c_format F32=1 [4,6); a_format [7,10), b_format [10,13) (0=f16, 1=bf16); a_major bit 15, b_major bit 16
 // (0 = K-major, 1 = MN-major); N>>3 [17,23); M>>4 [24,29).
@@ -236,6 +247,14 @@ __device__ __forceinline__ void tma_load_3d_e(void* smem_dst, const CUtensorMap*
       "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\t"
       "@P cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (size a multiple of 16 bytes), completing on an mbarrier like a TMA load
+__device__ __forceinline__ void bulk_load_1d_e(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\t"
+      "@P cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void mma_ss2_e(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,

@@ -191,7 +191,7 @@ struct FoldArgs {
 };
 template <typename T>
 __global__ void __launch_bounds__(256)
-fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf) {
+fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf, T* __restrict__ bt) {
   const int g = blockIdx.x, m = blockIdx.y;
   const int cin = a.c[0] + (a.nsrc > 1 ? a.c[1] : 0);
   __shared__ float s_a[512], s_s[512];          // per input column: scale and shift of its source channel
@@ -222,7 +222,22 @@ fold_weights_kernel(FoldArgs a, T* __restrict__ wf, float* __restrict__ bf) {
     float acc = 0.f;
     for (int col = lane; col < cin; col += 32) acc = fmaf(w[co * cin + col], s_s[col], acc);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) bf[((long)g * a.nmlp + m) * a.c_out + co] = a.b[m][co] + acc;
+    if (lane == 0) {
+      const float bias = a.b[m][co] + acc;
+      bf[((long)g * a.nmlp + m) * a.c_out + co] = bias;
+      if (bt) {
+        // the same bias as one K = 16 step of the first-layer MMA (conv-chain kernel): row n = m c_out + co of a
+        // K-major, un-swizzled B tile [n / 8][2 core matrices][8 rows][8 k]; k = 0 / 1 hold the 16-bit (hi, lo) split
+        const int nrow = m * a.c_out + co;
+        T* row = bt + (long)g * a.nmlp * a.c_out * 16 + (long)(nrow >> 3) * 128 + (nrow & 7) * 8;
+        const T hi = Elem<T>::from_float(bias);
+        const T lo = Elem<T>::from_float(bias - Elem<T>::to_float(hi));
+        row[0] = hi;
+        row[1] = lo;
+        for (int k = 2; k < 8; ++k) row[k] = Elem<T>::from_float(0.f);
+        for (int k = 0; k < 8; ++k) row[64 + k] = Elem<T>::from_float(0.f);
+      }
+    }
   }
 }
 
@@ -311,7 +326,8 @@ struct MlpArgs {
   Geo geo;
   int k_src[2], nsrc, K1, K1g;
   int depth, Kh;
-  const float* bias1;                        // [G][NMLP][COUT] folded layer-1 bias
+  const float* bias1;                        // [G][NMLP][COUT] folded layer-1 bias (fp32: RELU_OUT launches)
+  const T* bias1_tile;                       // [G][NMLP COUT / 8][2][8][8] the same as a K = 16 MMA step (depth > 1 launches)
   const float* bias[2][FGNN_MAX_DEPTH];      // per MLP, layer l >= 1 biases
   T* out[2];                                 // per MLP output planes (direct stores of the ones row only)
   int out_mode[2];                           // kOutC / kOutA / kOutB
@@ -331,16 +347,25 @@ constexpr int kMlpThreads = (kWL1 + 1) * 32;   // 576 -> 112 registers per threa
 constexpr int kMaxInStages = 4;
 __host__ __device__ inline int mlp_in_stages(int K1) { return K1 >= 128 ? 3 : 4; }   // 32 KB stages at K1 = 128
 
-// biases staged in shared memory: one folded first-layer bias vector per TMEM slot + the hidden layers' biases
+// fp32 biases staged in shared memory (RELU_OUT launches): one folded first-layer bias vector per TMEM slot
 __host__ __device__ inline size_t mlp_bias_floats(int COUT, int NMLP, int depth) {
-  return (size_t)kSlots * COUT + (size_t)NMLP * (depth > 2 ? depth - 2 : 0) * COUT;
+  return (size_t)kSlots * COUT;
+}
+
+// Biases through the tensor core (depth > 1): every conv whose output feeds a ReLU gets one extra K = 16 MMA step whose
+// A operand is a constant tile of ones (k = 0, 1) and whose B operand holds the bias as a 16-bit (hi, lo) pair --
+// the hidden pass is then a bare relu + pack.  Shared memory: the ones tile (4 KB), two buffers of the per-graph folded
+// first-layer bias tile, one tile per hidden layer that has a ReLU behind it.
+__host__ __device__ inline size_t mlp_bias_mma_bytes(int COUT, int NMLP, int depth) {
+  return depth > 1 ? (size_t)4096 + (size_t)2 * NMLP * COUT * 32 + (size_t)NMLP * (depth - 2) * COUT * 32 : 0;
 }
 
 template <int COUT, int NMLP>
 struct MlpSmem {
   static size_t bytes(int K1, int K1g, int depth, int Kh) {
     return 1024 + (size_t)mlp_in_stages(K1) * K1 * 256 + (size_t)2 * NMLP * K1g * COUT * 2 +
-           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)kSlots * COUT * 256 + mlp_bias_floats(COUT, NMLP, depth) * 4 + 512;
+           (size_t)NMLP * (depth - 1) * Kh * COUT * 2 + (size_t)kSlots * COUT * 256 + mlp_bias_mma_bytes(COUT, NMLP, depth) +
+           mlp_bias_floats(COUT, NMLP, depth) * 4 + 512;
   }
 };
 
@@ -351,8 +376,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
               const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
               const MlpArgs<T> args) {
   static_assert(kSlots % NMLP == 0, "a slot serves one MLP");
-  constexpr uint32_t kAccCols = kSlots * COUT, kHidCols = kSlots * COUT / 2;
-  constexpr uint32_t kTmemCols = (kAccCols + kHidCols <= 256) ? 256 : 512;
+  constexpr uint32_t kAccCols = kSlots * COUT, kHidW = COUT / 2 + 8;   // packed activations + the ones columns of the bias step
+  constexpr uint32_t kTmemCols = (kAccCols + kSlots * kHidW <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   // round the base up to 1024 bytes with POINTER arithmetic: an integer round trip makes the compiler treat everything
   // behind it as generic memory (LD.E / ST.E instead of LDS / STS)
@@ -370,9 +395,14 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   uint8_t* s_out = s_wh + (size_t)NMLP * (depth - 1) * wh_mat_bytes;   // [kSlots groups][2 halves][COUT][128 B] swizzled
   // Biases live in shared memory: with > 200 KB of it carved out the L1 holds next to nothing, and 16 global
   // loads per epilogue pass (uniform address, L2 latency) were costing more than the rest of the pass together.
-  float* s_bias1 = reinterpret_cast<float*>(s_out + (size_t)kSlots * COUT * 256);   // [kSlots][COUT] folded first-layer bias of the slot's graph
-  float* s_biash = s_bias1 + kSlots * COUT;                                         // [NMLP][depth-2][COUT] biases of layers 1 .. depth-2
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + (size_t)kSlots * COUT * 256 + mlp_bias_floats(COUT, NMLP, depth) * 4);
+  const bool bias_mma = depth > 1;                             // biases of the ReLU-ed layers ride on an extra MMA step
+  const uint32_t b1x_bytes = (uint32_t)NMLP * COUT * 32u;      // one graph's folded first-layer bias tile
+  uint8_t* s_ones = s_out + (size_t)kSlots * COUT * 256;       // [2 halves][16 k rows][128 B]: rows 0, 1 = ones (1024-byte aligned)
+  uint8_t* s_b1x = s_ones + (bias_mma ? 4096 : 0);             // [2 buffers][NMLP COUT / 8][2][128 B] un-swizzled K-major
+  uint8_t* s_bhx = s_b1x + (bias_mma ? 2 * b1x_bytes : 0);     // [NMLP][depth-2][COUT / 8][2][128 B]
+  // fp32 biases in shared memory serve the RELU_OUT launches (depth 1, training forward) only
+  float* s_bias1 = reinterpret_cast<float*>(s_out + (size_t)kSlots * COUT * 256 + mlp_bias_mma_bytes(COUT, NMLP, depth));   // [kSlots][COUT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias1) + mlp_bias_floats(COUT, NMLP, depth) * 4);
   uint64_t* in_full = bars;                      // [kInStages]
   uint64_t* in_empty = in_full + kMaxInStages;   // [kInStages]
   uint64_t* w1_full = in_empty + kMaxInStages;   // [2]
@@ -398,9 +428,21 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     for (int s = 0; s < kSlots; ++s) { mbar_init(&mma_done[s], 1); mbar_init(&acc_free[s], 4); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < NMLP * (depth - 2) * COUT; i += blockDim.x) {
-    const int c = i % COUT, ml = i / COUT;
-    s_biash[i] = args.bias[ml / (depth - 2)][1 + ml % (depth - 2)][c];
+  if (bias_mma) {
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x)      // ones tile: k rows 0 and 1 of both 64-pixel halves
+      reinterpret_cast<uint32_t*>(s_ones)[i] = (((i * 4) & 2047) < 256) ? Elem<T>::pack(1.f, 1.f) : 0u;
+    for (int i = threadIdx.x; i < NMLP * (depth - 2) * COUT; i += blockDim.x) {
+      const int c = i % COUT, ml = i / COUT;                  // ml = m (depth-2) + (layer - 1)
+      const float b = args.bias[ml / (depth - 2)][1 + ml % (depth - 2)][c];
+      const uint32_t hi = Elem<T>::bits(b);
+      const uint16_t hi16 = (uint16_t)hi;
+      const float hif = Elem<T>::to_float(*reinterpret_cast<const T*>(&hi16));
+      const uint32_t lo = Elem<T>::bits(b - hif);
+      uint4* row = reinterpret_cast<uint4*>(s_bhx + (size_t)ml * COUT * 32 + (size_t)(c >> 3) * 256 + (c & 7) * 16);
+      row[0] = make_uint4(hi | (lo << 16), 0u, 0u, 0u);        // k = 0, 1 of core matrix 0
+      row[8] = make_uint4(0u, 0u, 0u, 0u);                     // core matrix 1 (k = 8 .. 15), 128 bytes further
+    }
+    fence_proxy_async_smem();                                  // read by tcgen05.mma (async proxy)
   }
   if (warp == kWProd) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
@@ -453,7 +495,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         if (w.g != cur_g) {
           const int b = nchg & 1;
           if (nchg >= 2) { mbar_wait(&w1_empty[b], (ph_w1e >> b) & 1u); ph_w1e ^= 1u << b; }
-          mbar_arrive_expect_tx_e(&w1_full[b], w1_buf_bytes);
+          mbar_arrive_expect_tx_e(&w1_full[b], w1_buf_bytes + (bias_mma ? b1x_bytes : 0u));
+          if (bias_mma)
+            bulk_load_1d_e(s_b1x + (size_t)b * b1x_bytes, args.bias1_tile + (size_t)w.g * NMLP * COUT * 16, b1x_bytes, &w1_full[b]);
           for (int m = 0; m < NMLP; ++m)
             for (int at = 0; at < K1g / 64; ++at)
               tma_load_3d_e(s_w1 + (size_t)b * w1_buf_bytes + (size_t)m * w1_mlp_bytes + (size_t)at * COUT * 128,
@@ -488,6 +532,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       const uint64_t b_d0 = smem_desc_sw128(smem_u32(s_w1), 16u, 1024u);                   // K-major weights
       const uint32_t a_desc_lo0 = (uint32_t)a_d0, a_desc_hi = (uint32_t)(a_d0 >> 32);
       const uint32_t w1_desc_lo0 = (uint32_t)b_d0, b_desc_hi = (uint32_t)(b_d0 >> 32);
+      const uint64_t one_d = smem_desc_sw128(smem_u32(s_ones), 2048u, 1024u);              // ones tile, same format as a stage with K1 = 16
+      const uint64_t b1x_d0 = smem_desc_nosw(smem_u32(s_b1x), 128u, 256u);
+      const uint32_t one_lo = (uint32_t)one_d, one_hi = (uint32_t)(one_d >> 32);
+      const uint32_t b1x_lo0 = (uint32_t)b1x_d0, b1x_hi = (uint32_t)(b1x_d0 >> 32);
       Walker wi;
       walker_init(wi);
       walker_seek(wi, t_begin);
@@ -522,6 +570,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
               a_lo += 2048u >> 4;                                       // next 16 K-rows of the MN-major tile
               b_lo += 32u >> 4;                                         // next 32 B of the single K atom
             }
+            if (bias_mma) mma_ss2(d_tmem, one_lo, one_hi, b1x_lo0 + (((uint32_t)wbuf * b1x_bytes) >> 4), b1x_hi, idesc1w, 1u);
           } else {
 #pragma unroll 1
             for (int m = 0; m < NMLP; ++m) {
@@ -533,6 +582,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
                 a_lo += 2048u >> 4;
                 b_lo += ((k & 3) == 3) ? ((COUT * 128u - 96u) >> 4) : (32u >> 4);  // next K atom / next 32 B
               }
+              if (bias_mma)
+                mma_ss2(d_tmem, one_lo, one_hi, b1x_lo0 + (((uint32_t)wbuf * b1x_bytes + (uint32_t)m * COUT * 32u) >> 4), b1x_hi, idesc1, 1u);
             }
           }
           mma_commit(&in_empty[st]);
@@ -553,12 +604,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     const int m = s % NMLP;                  // the MLP this slot serves
     const int bar_id = 1 + s;
     const uint32_t acc_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * COUT);
-    const uint32_t hid_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + kAccCols + (uint32_t)(s * (COUT / 2));
+    const uint32_t hid_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + kAccCols + (uint32_t)s * kHidW;
     uint8_t* tile = s_out + (size_t)s * (COUT * 256);      // [half][COUT rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
-    const bool storer = !POOL && lane == 0 && quad < 2;    // lane 0 of the group's first two warps: one 64-pixel half each
+    const bool storer = !POOL && lane == 0 && (quad & 1) == 0;   // lane 0 of warps 0 / 2 of the group: its pixel starts a 64-pixel half
     const uint32_t idesc2 = make_idesc(Elem<T>::kFmt, 0, 0, kTileM, COUT);
     const uint32_t wh_desc_lo0 = (uint32_t)smem_desc_sw128(smem_u32(s_wh), 16u, 1024u);
     const uint32_t wh_desc_hi = (uint32_t)(smem_desc_sw128(smem_u32(s_wh), 16u, 1024u) >> 32);
+    const uint64_t bhx_d0 = smem_desc_nosw(smem_u32(s_bhx), 128u, 256u);
+    if (bias_mma) {
+      // the ones columns of this slot's TMEM A operand (k = COUT, COUT + 1 of the hidden layers' bias step): written once
+      uint32_t ones8[8] = {Elem<T>::pack(1.f, 1.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st8(hid_addr + (uint32_t)(COUT / 2), ones8);
+      tmem_wait_st();                          // ordered before the first hidden MMA by the pass's fence + named barrier
+    }
     uint32_t ph_mma = 0;                     // parity of mma_done[s]
     bool wh_ready = false;
     Walker w;
@@ -598,7 +656,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       const long seq = v / NMLP;
       walker_seek(w, t_begin + seq);
       const int g = w.g, n = w.n;
-      if ((depth > 1 || RELU_OUT) && g != bias_g) {
+      if (RELU_OUT && g != bias_g) {
         // first tile of a new graph in this slot.  Every warp of the group has passed a named barrier since it last
         // read s_bias1 (the barrier that ends the pass), so the vector may be overwritten.
         if (et < COUT) s_bias1[s * COUT + et] = __ldg(args.bias1 + ((long)g * NMLP + m) * COUT + et);
@@ -611,30 +669,19 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         mbar_wait(&mma_done[s], ph_mma);
         ph_mma ^= 1u;
         tc_fence_after();
-        const float* bias = (l == 0) ? (s_bias1 + s * COUT) : (s_biash + (m * (depth - 2) + (l - 1)) * COUT);
         {
-          // all accumulator columns in flight at once: one TMEM round trip per item instead of one per 32 columns;
-          // the biases of the first 32 columns are fetched from shared memory while that load is in flight
-          const uint32_t bias_s = smem_u32(bias);
+          // all accumulator columns in flight at once: one TMEM round trip per pass; the bias is already in the
+          // accumulator (extra MMA step), so the pass is relu + round + pack
           uint32_t r[COUT];
 #pragma unroll
           for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld32(acc_addr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
+          tmem_wait_ld();
 #pragma unroll
           for (int c0 = 0; c0 < COUT; c0 += 32) {
-            float4 bq[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) bq[u] = lds128(bias_s + (uint32_t)(c0 + 4 * u) * 4u);
-            if (c0 == 0) tmem_wait_ld();
             uint32_t h[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              float x0 = __uint_as_float(r[c0 + 4 * u]), x1 = __uint_as_float(r[c0 + 4 * u + 1]);
-              float x2 = __uint_as_float(r[c0 + 4 * u + 2]), x3 = __uint_as_float(r[c0 + 4 * u + 3]);
-              add2(x0, x1, bq[u].x, bq[u].y);
-              add2(x2, x3, bq[u].z, bq[u].w);
-              h[2 * u] = Elem<T>::pack_relu(x0, x1);
-              h[2 * u + 1] = Elem<T>::pack_relu(x2, x3);
-            }
+            for (int u = 0; u < 16; ++u)
+              h[u] = Elem<T>::pack_relu(__uint_as_float(r[c0 + 2 * u]), __uint_as_float(r[c0 + 2 * u + 1]));
             tmem_st16(hid_addr + (uint32_t)(c0 / 2), h);
           }
         }
@@ -648,7 +695,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           if (!wh_ready) { mbar_wait(wh_full, 0); wh_ready = true; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(s * COUT);
-          const uint32_t a_tmem = tmem_base + kAccCols + (uint32_t)(s * (COUT / 2));
+          const uint32_t a_tmem = tmem_base + kAccCols + (uint32_t)s * kHidW;
           const uint32_t wl_lo = wh_desc_lo0 + (uint32_t)(m * (depth - 1) + l) * (wh_mat_bytes >> 4);
           if (elect_one_sync()) {
 #pragma unroll
@@ -656,6 +703,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
               mma_ts2(d_tmem, a_tmem + (uint32_t)k * 8u,
                       wl_lo + (((uint32_t)(k / 4) * (COUT * 128u) + (uint32_t)(k % 4) * 32u) >> 4), wh_desc_hi, idesc2,
                       k > 0 ? 1u : 0u);
+            if (l + 1 <= depth - 2)              // this layer's output feeds a ReLU: its bias rides on one more K = 16 step
+              mma_ts2(d_tmem, a_tmem + (uint32_t)(COUT / 2),
+                      (uint32_t)bhx_d0 + (((uint32_t)(m * (depth - 2) + l) * COUT * 32u) >> 4), (uint32_t)(bhx_d0 >> 32), idesc2, 1u);
             mma_commit(&mma_done[s]);
           }
           __syncwarp();
@@ -752,10 +802,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       if (storer) {
         // store it: one 64-pixel half per TMA (a half never straddles a row because NPC % 64 == 0)
         const CUtensorMap* mo = (m == 0) ? &map_o0 : &map_o1;
-        const int ph = p0 + quad * 64;
-        const int prw = ph / geo.NPC, col = ph - prw * geo.NPC;
+        const int prw = pi, col = pj;
         const int prow = (mode == kOutA) ? prw + prw / kTM1 : (mode == kOutB ? prw + prw / geo.TN1 : prw);
-        if (prw < geo.N) tma_store_3d(mo, tile + (size_t)quad * (COUT * 128), col, prow, g * COUT);
+        if (prw < geo.N) tma_store_3d(mo, tile + (size_t)(quad >> 1) * (COUT * 128), col, prow, g * COUT);
         bulk_commit_group();
       }
       // ones rows of Y1 (layout A): the last logical row of every 127-row matmul tile writes the row below it
@@ -1228,6 +1277,7 @@ struct MlpLaunch {
   int nmlp;
   const T* w1f;        // [G][nmlp][COUT][K1g]
   const float* bias1;  // [G][nmlp][COUT]
+  const T* bias1_tile; // [G][nmlp COUT / 8][2][8][8] the folded bias as an MMA step (required when depth > 1)
   const T* wh;         // [nmlp][depth-1][COUT][Kh]
   const float* bias[2][FGNN_MAX_DEPTH];
   int depth, c_out;
@@ -1253,6 +1303,8 @@ int launch_mlp_t(const MlpLaunch<T>& L, int G, const Geo& geo, const int32_t* np
   a.depth = L.depth;
   a.Kh = COUT < 64 ? 64 : COUT;
   a.bias1 = L.bias1;
+  a.bias1_tile = L.bias1_tile;
+  FGNN_CHECK_ARG(L.depth == 1 || L.bias1_tile != nullptr, "conv chains with hidden layers need the folded bias tile");
   for (int m = 0; m < NMLP; ++m) {
     for (int l = 0; l < L.depth; ++l) a.bias[m][l] = L.bias[m][l];
     a.out[m] = L.out[m];
@@ -1334,6 +1386,7 @@ struct MlpGroup {
   int nsrc;
   T* wf;
   float* bf;
+  T* bt;             // [G][nmlp][C][16] folded first-layer bias as an MMA step (may be null for depth-1 launches)
   const T* wh;       // [nmlp][depth-1][C][Kh]
   T* out[2];
   int out_mode[2];
@@ -1362,7 +1415,7 @@ int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int3
   fa.c_out = C;
   fa.K1g = round_up(round_up(M.c_src[0], 16) + (M.nsrc > 1 ? round_up(M.c_src[1], 16) : 0), 64);
   FGNN_CHECK_ARG(fa.c[0] + fa.c[1] <= 512, "too many input channels for the fold kernel");
-  fold_weights_kernel<T><<<dim3(G, M.nmlp, 8), 256, 0, st>>>(fa, M.wf, M.bf);
+  fold_weights_kernel<T><<<dim3(G, M.nmlp, 8), 256, 0, st>>>(fa, M.wf, M.bf, M.bt);
   FGNN_LAUNCHED();
   MlpLaunch<T> L{};
   L.nmlp = M.nmlp;
@@ -1370,6 +1423,7 @@ int run_mlp_group(const MlpGroup<T>& M, int C, int G, const Geo& geo, const int3
   for (int s = 0; s < 2; ++s) { L.src[s] = M.src[s]; L.c_src[s] = M.c_src[s]; }
   L.w1f = M.wf;
   L.bias1 = M.bf;
+  L.bias1_tile = M.bt;
   L.wh = M.wh;
   L.depth = M.mp[0]->depth;
   L.c_out = C;
@@ -1453,6 +1507,7 @@ struct Buffers {
   float *coef1, *coef2, *coef3a, *coef3b;      // [chunk][C][2]
   void *wf12, *wf3;                            // folded first-layer weights
   float *bf12, *bf3;                           // folded first-layer biases
+  void *bt12, *bt3;                            // the same as 16-bit MMA-step tiles
   double* stat_acc;                            // [chunk][2][C][2]
   void* wh;                                    // [blocks][3][depth-1][C][Kh]
   unsigned int* rowenc;                        // [chunk][C][N][2] row max / min codes of the last block's output
@@ -1475,6 +1530,8 @@ size_t carve(const Plan& pl, int num_blocks, Arena& ar, Buffers& B) {
   B.wf3 = ar.take<uint16_t>(nc * pl.K1g3_max, 1024);
   B.bf12 = ar.take<float>(2 * nc);
   B.bf3 = ar.take<float>(nc);
+  B.bt12 = ar.take<uint16_t>(2 * nc * 16, 1024);
+  B.bt3 = ar.take<uint16_t>(nc * 16, 1024);
   B.stat_acc = ar.take<double>(4 * nc);
   const int Kh = pl.C < 64 ? 64 : pl.C;
   B.wh = ar.take<uint16_t>((size_t)num_blocks * 3 * std::max(pl.depth_max - 1, 1) * pl.C * Kh, 1024);
@@ -1543,7 +1600,7 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, const uint8_t* adj, 
         M.nmlp = 2;
         M.mp[0] = &bp.mlp1; M.mp[1] = &bp.mlp2;
         M.src[0] = cur; M.c_src[0] = cur_c; M.src_coef[0] = cur_coef; M.nsrc = 1;
-        M.wf = reinterpret_cast<T*>(B.wf12); M.bf = B.bf12;
+        M.wf = reinterpret_cast<T*>(B.wf12); M.bf = B.bf12; M.bt = reinterpret_cast<T*>(B.bt12);
         M.wh = whb;
         M.out[0] = y1; M.out_mode[0] = kOutA; M.ones[0] = 1; M.coef[0] = B.coef1;
         M.out[1] = y2; M.out_mode[1] = kOutB; M.ones[1] = 1; M.coef[1] = B.coef2;
@@ -1557,7 +1614,7 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, const uint8_t* adj, 
         M.mp[0] = &bp.mlp3;
         M.src[0] = mult; M.c_src[0] = C; M.src_coef[0] = nullptr;
         M.src[1] = cur; M.c_src[1] = cur_c; M.src_coef[1] = cur_coef; M.nsrc = 2;
-        M.wf = reinterpret_cast<T*>(B.wf3); M.bf = B.bf3;
+        M.wf = reinterpret_cast<T*>(B.wf3); M.bf = B.bf3; M.bt = reinterpret_cast<T*>(B.bt3);
         M.wh = whb + (size_t)2 * dm1 * C * Kh;
         M.out[0] = nxt; M.out_mode[0] = kOutC; M.ones[0] = 0; M.coef[0] = nxt_coef;
         M.stat_acc = B.stat_acc;
@@ -1690,7 +1747,7 @@ size_t debug_mlp_workspace_bytes(int G, int c_in, int c_out, int depth, int N) {
   const int K1g = round_up(round_up(c_in, 16), 64);
   const int Kh = c_out < 64 ? 64 : c_out;
   return align_up((size_t)G * (c_in + c_out) * geo.PSC * 2 + (size_t)G * c_out * K1g * 2 +
-                      (size_t)std::max(depth - 1, 1) * c_out * Kh * 2 + (size_t)G * c_out * (3 * 4 + 16) + 16384, 1024);
+                      (size_t)std::max(depth - 1, 1) * c_out * Kh * 2 + (size_t)G * c_out * (3 * 4 + 16 + 32) + 16384, 1024);
 }
 
 template <typename T>
@@ -1708,6 +1765,7 @@ int debug_mlp_t(const fgnn_mlp_params& mp, const float* x, float* y, int G, int 
   T* wf = ar.take<T>((size_t)G * C * K1g, 1024);
   T* wh = ar.take<T>((size_t)std::max(mp.depth - 1, 1) * C * Kh, 1024);
   float* bf = ar.take<float>((size_t)G * C);
+  T* bt = ar.take<T>((size_t)G * C * 16, 1024);
   float* coef = ar.take<float>((size_t)G * C * 2);
   double* acc = ar.take<double>((size_t)G * C * 2);
   {
@@ -1723,7 +1781,7 @@ int debug_mlp_t(const fgnn_mlp_params& mp, const float* x, float* y, int G, int 
   M.nmlp = 1;
   M.mp[0] = &mp;
   M.src[0] = xin; M.c_src[0] = mp.c_in; M.src_coef[0] = nullptr; M.nsrc = 1;
-  M.wf = wf; M.bf = bf; M.wh = wh;
+  M.wf = wf; M.bf = bf; M.bt = bt; M.wh = wh;
   M.out[0] = out; M.out_mode[0] = kOutC; M.ones[0] = 0; M.coef[0] = coef;
   M.stat_acc = acc;
   if (int e = run_mlp_group<T>(M, C, G, geo, npg, st)) return e;

@@ -7,14 +7,14 @@
 #include "../../graph_neural_net_b200/csrc/fgnn_ptx.cuh"
 using namespace fgnn::ptx;
 
-__global__ void __launch_bounds__(256, 1) bw_kernel(int nwarps, int iters, int mode, long long* out, uint32_t* sink) {
+__global__ void __launch_bounds__(512, 1) bw_kernel(int nwarps, int iters, int mode, long long* out, uint32_t* sink) {
   __shared__ uint32_t slot;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0) tmem_alloc(&slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+  const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128 % 512);
   uint32_t r[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) r[i] = lane + i;
@@ -57,13 +57,13 @@ __global__ void __launch_bounds__(256, 1) bw_kernel(int nwarps, int iters, int m
 int main() {
   long long* out;
   uint32_t* sink;
-  cudaMallocManaged(&out, 8 * sizeof(long long));
-  cudaMalloc(&sink, 256 * 4);
+  cudaMallocManaged(&out, 16 * sizeof(long long));
+  cudaMalloc(&sink, 512 * 4);
   const int iters = 2000;
   const char* names[4] = {"ld 32x32b.x64 (8 KB/warp)", "st 2 x 32x32b.x32 (8 KB/warp)", "ld 2 x 32x32b.x32 in flight (8 KB/warp)", "ld 2 x 16x256b.x8 (8 KB/warp)"};
   for (int mode = 0; mode < 4; ++mode)
-    for (int nw : {1, 2, 4, 8}) {
-      bw_kernel<<<1, 256>>>(nw, iters, mode, out, sink);
+    for (int nw : {1, 2, 4, 8, 16}) {
+      bw_kernel<<<1, 512>>>(nw, iters, mode, out, sink);
       if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
       long long mx = 0;
       for (int w = 0; w < nw; ++w) mx = out[w] > mx ? out[w] : mx;
