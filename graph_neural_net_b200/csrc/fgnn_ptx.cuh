@@ -148,6 +148,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// register hand-over between warp groups (all four warps of an aligned group of four execute the same instruction)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- tcgen05: descriptors ---------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle.  Fields (bits): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), base_offset [49,52)=0, layout_type [61,64)=2 (SWIZZLE_128B).
@@ -354,6 +358,10 @@ __device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, uint32_t r0, u
   asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
                ::"r"(saddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
                : "memory");
+}
+// two transposed 8x8 b16 matrices: row r of matrix i goes to the address supplied by thread 8i + r (threads 0-15)
+__device__ __forceinline__ void stmatrix_x2_trans(uint32_t saddr, uint32_t r0, uint32_t r1) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(saddr), "r"(r0), "r"(r1) : "memory");
 }
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
   asm volatile(

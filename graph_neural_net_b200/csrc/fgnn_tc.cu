@@ -25,6 +25,7 @@
 #include "fgnn_ptx.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 
@@ -342,7 +343,10 @@ struct MlpArgs {
 
 constexpr int kSlots = 4;                    // TMEM slots = epilogue groups
 constexpr int kWProd = 4 * kSlots, kWL1 = kWProd + 1;
-constexpr int kMlpThreads = (kWL1 + 1) * 32;   // 576 -> 112 registers per thread
+// 18 warps; registers are allocated in units of four warps, so the kernel gets 96 registers per thread (as 20 warps would).
+// (setmaxnreg hand-over from the control warps to the epilogue groups was tried: ptxas 12.9 then allocates the WHOLE
+// kernel at the smallest setmaxnreg value -- every role spilled.)
+constexpr int kMlpThreads = (kWL1 + 1) * 32;
 
 constexpr int kMaxInStages = 4;
 __host__ __device__ inline int mlp_in_stages(int K1) { return K1 >= 128 ? 3 : 4; }   // 32 KB stages at K1 = 128
@@ -630,6 +634,32 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     const int half = (part * kPxPerPart) / 64, chunk0 = ((part * kPxPerPart) % 64) / 8;
     float acc_s = 0.f, acc_q = 0.f;
     int acc_g = -1;
+    // register statistics (all but the pooled launches): sums of this thread's 16 (COUT = 64) channels over its pixels
+    constexpr bool kRegStats = !POOL;
+    float st_S[COUT / 4], st_Q[COUT / 4];
+#pragma unroll
+    for (int i = 0; i < COUT / 4; ++i) { st_S[i] = 0.f; st_Q[i] = 0.f; }
+    auto flush_reg = [&]() {
+      // the eight lanes with equal lane % 4 hold the same channels: fold them, then lanes 0-3 publish (warp-uniform call)
+      if (acc_g < 0) return;
+#pragma unroll
+      for (int i = 0; i < COUT / 4; ++i) {
+        float sv = st_S[i], qv = st_Q[i];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          sv += __shfl_xor_sync(0xffffffffu, sv, o);
+          qv += __shfl_xor_sync(0xffffffffu, qv, o);
+        }
+        if (lane < 4) {
+          const int ch = 8 * (i >> 1) + 2 * lane + (i & 1);
+          double* dst = args.stat_acc + (((long)acc_g * NMLP + m) * COUT + ch) * 2;
+          atomicAdd(dst, (double)sv);
+          atomicAdd(dst + 1, (double)qv);
+        }
+        st_S[i] = 0.f;
+        st_Q[i] = 0.f;
+      }
+    };
     auto flush = [&]() {
       if (acc_g < 0) return;
       double* dst = args.stat_acc + (((long)acc_g * NMLP + m) * COUT + c) * 2;
@@ -670,18 +700,17 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         ph_mma ^= 1u;
         tc_fence_after();
         {
-          // all accumulator columns in flight at once: one TMEM round trip per pass; the bias is already in the
-          // accumulator (extra MMA step), so the pass is relu + round + pack
-          uint32_t r[COUT];
-#pragma unroll
-          for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld32(acc_addr + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
-          tmem_wait_ld();
+          // the bias is already in the accumulator (extra MMA step), so the pass is relu + round + pack; 32 columns per
+          // round (the epilogue warps also carry the statistics accumulators: registers)
 #pragma unroll
           for (int c0 = 0; c0 < COUT; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(acc_addr + (uint32_t)c0, r);
+            tmem_wait_ld();
             uint32_t h[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u)
-              h[u] = Elem<T>::pack_relu(__uint_as_float(r[c0 + 2 * u]), __uint_as_float(r[c0 + 2 * u + 1]));
+              h[u] = Elem<T>::pack_relu(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1]));
             tmem_st16(hid_addr + (uint32_t)(c0 / 2), h);
           }
         }
@@ -735,66 +764,84 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       {
         // Transposing store: the 16x256b TMEM load hands every thread channel PAIRS of four pixels (the mma
         // C-fragment layout), one packed convert per pair, and stmatrix.trans writes 8 channels x 8 pixels as
-        // eight 16-byte row pieces -> 8 stmatrix per warp instead of 64 two-byte stores per thread.
+        // eight 16-byte row pieces.  Two rounds of 16 TMEM lanes each (registers): round hr covers the warp's pixels
+        // 16 hr + lane / 4 (registers 4u, 4u+1) and 16 hr + 8 + lane / 4 (registers 4u+2, 4u+3), channels
+        // 8u + 2 (lane % 4), +1.  The GraphNorm statistics are taken from the fp32 accumulators in the same pass:
+        // every thread keeps the sum and the sum of squares of its 16 channels over its pixels in registers.
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         const uint32_t mmask = __ballot_sync(0xffffffffu, marker != 0.f);
-        uint32_t rl[COUT / 2], ru[COUT / 2];
-        if constexpr (COUT == 64) {
-          tmem_ld_16x256b_x8(acc_addr, rl);
-          tmem_ld_16x256b_x8(acc_addr + (16u << 16), ru);
-        } else {
-          tmem_ld_16x256b_x4(acc_addr, rl);
-          tmem_ld_16x256b_x4(acc_addr + (16u << 16), ru);
-        }
         const int q4 = lane >> 2;
         const uint32_t one2 = Elem<T>::pack(1.f, 1.f);
-        bool vb[4];
-        uint32_t fill[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          vb[i] = (vmask >> (8 * i + q4)) & 1u;
-          fill[i] = ((mmask >> (8 * i + q4)) & 1u) ? one2 : 0u;
+        if constexpr (kRegStats) {
+          if (g != acc_g) { flush_reg(); acc_g = g; }
         }
-        // this thread supplies the address of row (lane % 8) of matrix (lane / 8): channel 8u + lane % 8,
-        // pixels quad * 32 + 8 * (lane / 8) .. + 7 = 16-byte chunk (quad & 1) * 4 + lane / 8 of half quad / 2
-        const uint32_t st_addr = smem_u32(tile) + (uint32_t)(quad >> 1) * (COUT * 128) + (uint32_t)(lane & 7) * 128 +
-                                 (uint32_t)(((((quad & 1) << 2) + (lane >> 3)) ^ (lane & 7)) << 4);
-        tmem_wait_ld();
-        tc_fence_before();                 // accumulator drained: the slot may take its next tile
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_free[s]);
-        if constexpr (RELU_OUT) {
-          // training forward, every conv layer is its own depth-1 launch: out = relu(acc + bias), bias of this
-          // thread's channel pair 8u + 2 * (lane % 4), +1 from the slot's folded first-layer bias
-          const float* bsl = s_bias1 + s * COUT + 2 * (lane & 3);     // RELU_OUT launches have depth == 1
+        // this thread supplies the address of row (lane % 8) of matrix (lane / 8) % 2: channel 8u + lane % 8,
+        // pixels quad * 32 + 16 hr + 8 ((lane / 8) % 2) .. + 7 = 16-byte chunk (quad & 1) * 4 + 2 hr + (lane / 8) % 2
+        const uint32_t st_base = smem_u32(tile) + (uint32_t)(quad >> 1) * (COUT * 128) + (uint32_t)(lane & 7) * 128;
+        auto round = [&](auto all_valid_tag, int hr) {
+          constexpr bool kAllValid = decltype(all_valid_tag)::value;
+          uint32_t r[COUT / 2];
+          if constexpr (COUT == 64) tmem_ld_16x256b_x8(acc_addr + ((uint32_t)(16 * hr) << 16), r);
+          else tmem_ld_16x256b_x4(acc_addr + ((uint32_t)(16 * hr) << 16), r);
+          const uint32_t st_addr = st_base + (uint32_t)(((((quad & 1) << 2) + 2 * hr + ((lane >> 3) & 1)) ^ (lane & 7)) << 4);
+          const bool va = (vmask >> (16 * hr + q4)) & 1u, vb = (vmask >> (16 * hr + 8 + q4)) & 1u;
+          const uint32_t fa = ((mmask >> (16 * hr + q4)) & 1u) ? one2 : 0u, fb = ((mmask >> (16 * hr + 8 + q4)) & 1u) ? one2 : 0u;
+          tmem_wait_ld();
+          if (hr == 1) {
+            tc_fence_before();                 // accumulator drained: the slot may take its next tile
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[s]);
+          }
+          if constexpr (RELU_OUT) {
+            // training forward, every conv layer is its own depth-1 launch: out = relu(acc + bias), bias of this
+            // thread's channel pair 8u + 2 * (lane % 4), +1 from the slot's folded first-layer bias
+            const float* bsl = s_bias1 + s * COUT + 2 * (lane & 3);     // RELU_OUT launches have depth == 1
+#pragma unroll
+            for (int u = 0; u < COUT / 8; ++u) {
+              const float2 bb = *reinterpret_cast<const float2*>(bsl + 8 * u);
+              r[4 * u] = __float_as_uint(__uint_as_float(r[4 * u]) + bb.x);
+              r[4 * u + 1] = __float_as_uint(__uint_as_float(r[4 * u + 1]) + bb.y);
+              r[4 * u + 2] = __float_as_uint(__uint_as_float(r[4 * u + 2]) + bb.x);
+              r[4 * u + 3] = __float_as_uint(__uint_as_float(r[4 * u + 3]) + bb.y);
+            }
+          }
+          if constexpr (kRegStats) {
+            if constexpr (!kAllValid) {
+#pragma unroll
+              for (int u = 0; u < COUT / 8; ++u) {
+                if (!va) { r[4 * u] = 0u; r[4 * u + 1] = 0u; }
+                if (!vb) { r[4 * u + 2] = 0u; r[4 * u + 3] = 0u; }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < COUT / 8; ++u) {
+              sum_sq2(st_S[2 * u], st_S[2 * u + 1], st_Q[2 * u], st_Q[2 * u + 1], __uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]));
+              sum_sq2(st_S[2 * u], st_S[2 * u + 1], st_Q[2 * u], st_Q[2 * u + 1], __uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3]));
+            }
+          }
 #pragma unroll
           for (int u = 0; u < COUT / 8; ++u) {
-            const float2 bb = *reinterpret_cast<const float2*>(bsl + 8 * u);
-            rl[4 * u] = __float_as_uint(__uint_as_float(rl[4 * u]) + bb.x);
-            rl[4 * u + 1] = __float_as_uint(__uint_as_float(rl[4 * u + 1]) + bb.y);
-            rl[4 * u + 2] = __float_as_uint(__uint_as_float(rl[4 * u + 2]) + bb.x);
-            rl[4 * u + 3] = __float_as_uint(__uint_as_float(rl[4 * u + 3]) + bb.y);
-            ru[4 * u] = __float_as_uint(__uint_as_float(ru[4 * u]) + bb.x);
-            ru[4 * u + 1] = __float_as_uint(__uint_as_float(ru[4 * u + 1]) + bb.y);
-            ru[4 * u + 2] = __float_as_uint(__uint_as_float(ru[4 * u + 2]) + bb.x);
-            ru[4 * u + 3] = __float_as_uint(__uint_as_float(ru[4 * u + 3]) + bb.y);
+            uint32_t w0, w1;
+            if constexpr (RELU_OUT) {
+              w0 = Elem<T>::pack_relu(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]));
+              w1 = Elem<T>::pack_relu(__uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3]));
+            } else {
+              w0 = Elem<T>::pack(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]));
+              w1 = Elem<T>::pack(__uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3]));
+            }
+            if constexpr (!kAllValid) {
+              w0 = va ? w0 : fa;
+              w1 = vb ? w1 : fb;
+            }
+            stmatrix_x2_trans(st_addr + (uint32_t)u * 1024u, w0, w1);
           }
-        }
-#pragma unroll
-        for (int u = 0; u < COUT / 8; ++u) {
-          if constexpr (RELU_OUT) {
-            const uint32_t w0 = vb[0] ? Elem<T>::pack_relu(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
-            const uint32_t w1 = vb[1] ? Elem<T>::pack_relu(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
-            const uint32_t w2 = vb[2] ? Elem<T>::pack_relu(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
-            const uint32_t w3 = vb[3] ? Elem<T>::pack_relu(__uint_as_float(ru[4 * u + 2]), __uint_as_float(ru[4 * u + 3])) : fill[3];
-            stmatrix_x4_trans(st_addr + (uint32_t)u * 1024u, w0, w1, w2, w3);
-            continue;
-          }
-          const uint32_t w0 = vb[0] ? Elem<T>::pack(__uint_as_float(rl[4 * u]), __uint_as_float(rl[4 * u + 1])) : fill[0];
-          const uint32_t w1 = vb[1] ? Elem<T>::pack(__uint_as_float(rl[4 * u + 2]), __uint_as_float(rl[4 * u + 3])) : fill[1];
-          const uint32_t w2 = vb[2] ? Elem<T>::pack(__uint_as_float(ru[4 * u]), __uint_as_float(ru[4 * u + 1])) : fill[2];
-          const uint32_t w3 = vb[3] ? Elem<T>::pack(__uint_as_float(ru[4 * u + 2]), __uint_as_float(ru[4 * u + 3])) : fill[3];
-          stmatrix_x4_trans(st_addr + (uint32_t)u * 1024u, w0, w1, w2, w3);
+        };
+        if (vmask == 0xffffffffu) {
+          round(std::true_type{}, 0);
+          round(std::true_type{}, 1);
+        } else {
+          round(std::false_type{}, 0);
+          round(std::false_type{}, 1);
         }
       }
       fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -817,6 +864,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         }
       }
       // ---------------- statistics of the staged tile: sum / sum of squares per channel (+ row max / min) ----------------
+      if constexpr (!kRegStats) {
       if (g != acc_g) { flush(); acc_g = g; }
       {
         const uint8_t* row = tile + (size_t)half * (COUT * 128) + (size_t)c * 128;
@@ -901,10 +949,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           pool_mn = mn;
         }
       }
+      }
     }
     if (POOL && pool_row >= 0) pool_flush();
     if (storer) bulk_wait_group0();   // every store has landed before the CTA exits
-    flush();
+    if constexpr (kRegStats) flush_reg(); else flush();
   }
   tc_fence_before();
   __syncthreads();
