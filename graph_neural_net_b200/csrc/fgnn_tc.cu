@@ -84,8 +84,9 @@ __device__ __forceinline__ int rows_cover(const int32_t* n_per_graph, int g, con
   int r = (phys_k_end(n_per_graph[g], geo.TN1) + 63) / 64 * 64;
   return r < geo.N ? r : geo.N;
 }
-__device__ __forceinline__ long mlp_tiles(const int32_t* n_per_graph, int g, const Geo& geo) {
-  return ((long)rows_cover(n_per_graph, g, geo) * geo.NPC + kTileM - 1) / kTileM;
+// (32-bit tile arithmetic: a plane has at most 1024 x 1280 physical pixels, a launch at most 65535 planes' worth of tiles)
+__device__ __forceinline__ int mlp_tiles(const int32_t* n_per_graph, int g, const Geo& geo) {
+  return (rows_cover(n_per_graph, g, geo) * geo.NPC + kTileM - 1) / kTileM;
 }
 
 // =============================================================================================
@@ -348,6 +349,17 @@ constexpr int kWProd = 4 * kSlots, kWL1 = kWProd + 1;
 // kernel at the smallest setmaxnreg value -- every role spilled.)
 constexpr int kMlpThreads = (kWL1 + 1) * 32;
 
+// Optional cycle accounting of one epilogue warp and the first-layer issuer (compile with -DFGNN_TC_TIMING; bring-up only).
+#ifdef FGNN_TC_TIMING
+__device__ unsigned long long g_tc_timing[32];
+#define TIMING_DECL long long tm_t0 = clock64(), tm_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define TIMING_MARK(slot) do { long long tm_t1 = clock64(); tm_acc[slot] += tm_t1 - tm_t0; tm_t0 = tm_t1; } while (0)
+#define TIMING_FLUSH(base, cond) do { if (cond) for (int tm_i = 0; tm_i < 12; ++tm_i) atomicAdd(&g_tc_timing[(base) + tm_i], (unsigned long long)tm_acc[tm_i]); } while (0)
+#else
+#define TIMING_DECL
+#define TIMING_MARK(slot)
+#define TIMING_FLUSH(base, cond)
+#endif
 constexpr int kMaxInStages = 4;
 __host__ __device__ inline int mlp_in_stages(int K1) { return K1 >= 128 ? 3 : 4; }   // 32 KB stages at K1 = 128
 
@@ -419,11 +431,11 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
 
   // ---- tile range of this CTA: contiguous chunk of the flat (graph, tile) list ----------------
-  long total = 0;
+  int total = 0;
   for (int g = 0; g < args.G; ++g) total += mlp_tiles(args.n_per_graph, g, geo);
-  const long t_begin = total * blockIdx.x / gridDim.x;
-  const long t_end = total * (blockIdx.x + 1) / gridDim.x;
-  const long V = (t_end - t_begin) * NMLP;  // virtual tiles of this CTA
+  const int t_begin = (int)((long)total * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long)total * (blockIdx.x + 1) / gridDim.x);
+  const int V = (t_end - t_begin) * NMLP;  // virtual tiles of this CTA
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kInStages; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
@@ -457,7 +469,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
   // graph walker shared by all roles: flat tile t -> (graph g, first pixel p0); t must not decrease
   struct Walker {
     int g = 0, n = 0;
-    long base = 0, tiles = 0;
+    int base = 0, tiles = 0;
   };
   auto walker_init = [&](Walker& w) {
     w.g = 0;
@@ -465,7 +477,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
     w.n = graph_n(args.n_per_graph, 0, geo.N);
     w.tiles = mlp_tiles(args.n_per_graph, 0, geo);
   };
-  auto walker_seek = [&](Walker& w, long t) {
+  auto walker_seek = [&](Walker& w, int t) {
     while (t >= w.base + w.tiles) {
       w.base += w.tiles;
       ++w.g;
@@ -494,7 +506,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       walker_init(w);
       int cur_g = -1, nchg = 0;
       uint32_t ph_w1e = 0, ph_ine = 0;   // phase bits (bit i = parity to wait for on barrier i): registers, not arrays
-      for (long t = t_begin; t < t_end; ++t) {
+      for (int t = t_begin; t < t_end; ++t) {
         walker_seek(w, t);
         if (w.g != cur_g) {
           const int b = nchg & 1;
@@ -509,8 +521,8 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           cur_g = w.g;
           ++nchg;
         }
-        const long seq = t - t_begin;
-        const int st = (int)(seq % kInStages);
+        const int seq = t - t_begin;
+        const int st = seq % kInStages;
         if (seq >= kInStages) { mbar_wait(&in_empty[st], (ph_ine >> st) & 1u); ph_ine ^= 1u << st; }
         const int p0 = (int)((t - w.base) * kTileM);
         uint8_t* dst = s_in + (size_t)st * stage_bytes;
@@ -546,21 +558,26 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       const int g_first = wi.g;
       int issue_gidx = 0;                      // graphs (relative to g_first) whose weight buffer has been released
       uint32_t ph_free = 0;                    // phase bits of acc_free[s]
-      const long ntiles = t_end - t_begin;
-      for (long seq = 0; seq < ntiles; ++seq) {
+      const int ntiles = t_end - t_begin;
+      TIMING_DECL;
+      for (int seq = 0; seq < ntiles; ++seq) {
+        TIMING_MARK(0);
         const int st = (int)(seq % kInStages);
         walker_seek(wi, t_begin + seq);
         const int gidx = wi.g - g_first;
         for (; issue_gidx < gidx; ++issue_gidx) mma_commit_e(&w1_empty[issue_gidx & 1]);   // every MMA that read it was issued
         const int wbuf = gidx & 1;
         mbar_wait(&w1_full[wbuf], (uint32_t)(gidx >> 1) & 1u);
+        TIMING_MARK(1);
         mbar_wait(&in_full[st], (uint32_t)(seq / kInStages) & 1u);
+        TIMING_MARK(2);
         const int s0 = (int)((seq * NMLP) % kSlots);
 #pragma unroll
         for (int m = 0; m < NMLP; ++m) {
           if (seq * NMLP + m >= kSlots) { mbar_wait(&acc_free[s0 + m], (ph_free >> (s0 + m)) & 1u); ph_free ^= 1u << (s0 + m); }
         }
         tc_fence_after();
+        TIMING_MARK(3);
         const uint32_t a_lo0 = a_desc_lo0 + (uint32_t)st * (stage_bytes >> 4);
         const uint32_t b_lo0 = w1_desc_lo0 + (((uint32_t)wbuf * w1_buf_bytes) >> 4);
         if (elect_one_sync()) {
@@ -595,7 +612,9 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           for (int m = 0; m < NMLP; ++m) mma_commit(&mma_done[s0 + m]);
         }
         __syncwarp();
+        TIMING_MARK(4);
       }
+      TIMING_FLUSH(16, lane == 0);
       Walker wl = wi;                          // the producer may still wait for the release of later graphs
       walker_seek(wl, t_end - 1);
       for (; issue_gidx < wl.g - g_first + 1; ++issue_gidx) mma_commit_e(&w1_empty[issue_gidx & 1]);
@@ -682,10 +701,23 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       pool_mn = INFINITY;
     };
 
-    for (long v = s; v < V; v += kSlots) {
-      const long seq = v / NMLP;
+    TIMING_DECL;
+    int cur_g = -1, tp_i = 0, tp_j = 0;      // pixel (row, physical column) of the current tile's first pixel
+    for (int v = s; v < V; v += kSlots) {
+      TIMING_MARK(10);
+      const int seq = v / NMLP;
       walker_seek(w, t_begin + seq);
       const int g = w.g, n = w.n;
+      // tile position without a division per tile: this group's tiles are kSlots / NMLP apart inside a graph
+      const int p0 = (t_begin + seq - w.base) * kTileM;
+      if (g != cur_g) {
+        tp_i = p0 / geo.NPC;
+        tp_j = p0 - tp_i * geo.NPC;
+        cur_g = g;
+      } else {
+        tp_j += (kSlots / NMLP) * kTileM;
+        while (tp_j >= geo.NPC) { tp_j -= geo.NPC; ++tp_i; }
+      }
       if (RELU_OUT && g != bias_g) {
         // first tile of a new graph in this slot.  Every warp of the group has passed a named barrier since it last
         // read s_bias1 (the barrier that ends the pass), so the vector may be overwritten.
@@ -696,29 +728,33 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
 #pragma unroll 1
       for (int l = 0; l < depth - 1; ++l) {
         // ---------------- hidden pass: accumulator -> relu(acc + b) as the next layer's 16-bit A operand in TMEM ----------------
+        TIMING_MARK(0);
         mbar_wait(&mma_done[s], ph_mma);
         ph_mma ^= 1u;
         tc_fence_after();
+        TIMING_MARK(1);
         {
           // the bias is already in the accumulator (extra MMA step), so the pass is relu + round + pack; 32 columns per
           // round (the epilogue warps also carry the statistics accumulators: registers)
 #pragma unroll
-          for (int c0 = 0; c0 < COUT; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(acc_addr + (uint32_t)c0, r);
+          for (int c0 = 0; c0 < COUT; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(acc_addr + (uint32_t)c0, r);
             tmem_wait_ld();
-            uint32_t h[16];
+            uint32_t h[8];
 #pragma unroll
-            for (int u = 0; u < 16; ++u)
+            for (int u = 0; u < 8; ++u)
               h[u] = Elem<T>::pack_relu(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1]));
-            tmem_st16(hid_addr + (uint32_t)(c0 / 2), h);
+            tmem_st8(hid_addr + (uint32_t)(c0 / 2), h);
           }
         }
         tmem_wait_st();
         tc_fence_before();
         // the staging buffer must be free before the final pass: the store of this group's previous tile has read it
         if (l == depth - 2 && storer) bulk_wait_group_read0();
+        TIMING_MARK(2);
         named_bar_sync(bar_id, 128);           // all four quadrants of the operand are written (and fenced)
+        TIMING_MARK(3);
         if (quad == 0) {
           // this group issues its own next layer: A = packed activations in TMEM, B = the layer's weights in smem
           if (!wh_ready) { mbar_wait(wh_full, 0); wh_ready = true; }
@@ -739,6 +775,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           }
           __syncwarp();
         }
+        TIMING_MARK(4);
       }
       // ---------------- final pass: raw accumulator -> staged 16-bit tile -> TMA store + statistics ----------------
       if (depth == 1) {                        // (with hidden layers the last hidden pass's barrier covers this)
@@ -748,10 +785,10 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       mbar_wait(&mma_done[s], ph_mma);
       ph_mma ^= 1u;
       tc_fence_after();
-      // pixel coordinates with 32-bit arithmetic: one division per tile, then at most two row wraps
-      const int p0 = (int)(t_begin + seq - w.base) * kTileM;
-      int pi = p0 / geo.NPC;
-      int pj = p0 - pi * geo.NPC + et;
+      TIMING_MARK(5);
+      // pixel coordinates: at most two row wraps from the tile's first pixel
+      int pi = tp_i;
+      int pj = tp_j + et;
       if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
       if (pj >= geo.NPC) { pj -= geo.NPC; ++pi; }
       const bool in_plane = pi < geo.N;
@@ -778,26 +815,27 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         // this thread supplies the address of row (lane % 8) of matrix (lane / 8) % 2: channel 8u + lane % 8,
         // pixels quad * 32 + 16 hr + 8 ((lane / 8) % 2) .. + 7 = 16-byte chunk (quad & 1) * 4 + 2 hr + (lane / 8) % 2
         const uint32_t st_base = smem_u32(tile) + (uint32_t)(quad >> 1) * (COUT * 128) + (uint32_t)(lane & 7) * 128;
-        auto round = [&](auto all_valid_tag, int hr) {
+        auto round = [&](auto all_valid_tag, int hr, int cq) {
+          // 16 TMEM lanes x 32 columns per round: 16 registers in flight next to the 2 x COUT / 4 statistics accumulators
           constexpr bool kAllValid = decltype(all_valid_tag)::value;
-          uint32_t r[COUT / 2];
-          if constexpr (COUT == 64) tmem_ld_16x256b_x8(acc_addr + ((uint32_t)(16 * hr) << 16), r);
-          else tmem_ld_16x256b_x4(acc_addr + ((uint32_t)(16 * hr) << 16), r);
-          const uint32_t st_addr = st_base + (uint32_t)(((((quad & 1) << 2) + 2 * hr + ((lane >> 3) & 1)) ^ (lane & 7)) << 4);
+          uint32_t r[16];
+          tmem_ld_16x256b_x4(acc_addr + ((uint32_t)(16 * hr) << 16) + (uint32_t)(32 * cq), r);
+          const uint32_t st_addr = st_base + (uint32_t)(((((quad & 1) << 2) + 2 * hr + ((lane >> 3) & 1)) ^ (lane & 7)) << 4) +
+                                   (uint32_t)cq * 4096u;
           const bool va = (vmask >> (16 * hr + q4)) & 1u, vb = (vmask >> (16 * hr + 8 + q4)) & 1u;
           const uint32_t fa = ((mmask >> (16 * hr + q4)) & 1u) ? one2 : 0u, fb = ((mmask >> (16 * hr + 8 + q4)) & 1u) ? one2 : 0u;
           tmem_wait_ld();
-          if (hr == 1) {
+          if (hr == 1 && cq == COUT / 32 - 1) {
             tc_fence_before();                 // accumulator drained: the slot may take its next tile
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[s]);
           }
           if constexpr (RELU_OUT) {
             // training forward, every conv layer is its own depth-1 launch: out = relu(acc + bias), bias of this
-            // thread's channel pair 8u + 2 * (lane % 4), +1 from the slot's folded first-layer bias
-            const float* bsl = s_bias1 + s * COUT + 2 * (lane & 3);     // RELU_OUT launches have depth == 1
+            // thread's channel pair 32 cq + 8u + 2 * (lane % 4), +1 from the slot's folded first-layer bias
+            const float* bsl = s_bias1 + s * COUT + 32 * cq + 2 * (lane & 3);     // RELU_OUT launches have depth == 1
 #pragma unroll
-            for (int u = 0; u < COUT / 8; ++u) {
+            for (int u = 0; u < 4; ++u) {
               const float2 bb = *reinterpret_cast<const float2*>(bsl + 8 * u);
               r[4 * u] = __float_as_uint(__uint_as_float(r[4 * u]) + bb.x);
               r[4 * u + 1] = __float_as_uint(__uint_as_float(r[4 * u + 1]) + bb.y);
@@ -808,19 +846,20 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           if constexpr (kRegStats) {
             if constexpr (!kAllValid) {
 #pragma unroll
-              for (int u = 0; u < COUT / 8; ++u) {
+              for (int u = 0; u < 4; ++u) {
                 if (!va) { r[4 * u] = 0u; r[4 * u + 1] = 0u; }
                 if (!vb) { r[4 * u + 2] = 0u; r[4 * u + 3] = 0u; }
               }
             }
 #pragma unroll
-            for (int u = 0; u < COUT / 8; ++u) {
-              sum_sq2(st_S[2 * u], st_S[2 * u + 1], st_Q[2 * u], st_Q[2 * u + 1], __uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]));
-              sum_sq2(st_S[2 * u], st_S[2 * u + 1], st_Q[2 * u], st_Q[2 * u + 1], __uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3]));
+            for (int u = 0; u < 4; ++u) {
+              const int a = 8 * cq + 2 * u;
+              sum_sq2(st_S[a], st_S[a + 1], st_Q[a], st_Q[a + 1], __uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]));
+              sum_sq2(st_S[a], st_S[a + 1], st_Q[a], st_Q[a + 1], __uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 3]));
             }
           }
 #pragma unroll
-          for (int u = 0; u < COUT / 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             uint32_t w0, w1;
             if constexpr (RELU_OUT) {
               w0 = Elem<T>::pack_relu(__uint_as_float(r[4 * u]), __uint_as_float(r[4 * u + 1]));
@@ -837,15 +876,21 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           }
         };
         if (vmask == 0xffffffffu) {
-          round(std::true_type{}, 0);
-          round(std::true_type{}, 1);
+#pragma unroll
+          for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+            for (int cq = 0; cq < COUT / 32; ++cq) round(std::true_type{}, hr, cq);
         } else {
-          round(std::false_type{}, 0);
-          round(std::false_type{}, 1);
+#pragma unroll
+          for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+            for (int cq = 0; cq < COUT / 32; ++cq) round(std::false_type{}, hr, cq);
         }
       }
+      TIMING_MARK(6);
       fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
       named_bar_sync(bar_id, 128);         // the tile is staged
+      TIMING_MARK(7);
       if (storer) {
         // store it: one 64-pixel half per TMA (a half never straddles a row because NPC % 64 == 0)
         const CUtensorMap* mo = (m == 0) ? &map_o0 : &map_o1;
@@ -854,6 +899,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
         if (prw < geo.N) tma_store_3d(mo, tile + (size_t)(quad >> 1) * (COUT * 128), col, prow, g * COUT);
         bulk_commit_group();
       }
+      TIMING_MARK(8);
       // ones rows of Y1 (layout A): the last logical row of every 127-row matmul tile writes the row below it
       if (mode == kOutA && args.ones[m] && in_plane && pi < n) {
         const int mt = pi / kTM1;
@@ -863,6 +909,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
           for (int cc = 0; cc < COUT; ++cc) o1[(long)cc * geo.PSA] = ov;
         }
       }
+      TIMING_MARK(9);
       // ---------------- statistics of the staged tile: sum / sum of squares per channel (+ row max / min) ----------------
       if constexpr (!kRegStats) {
       if (g != acc_g) { flush(); acc_g = g; }
@@ -951,6 +998,7 @@ tc_mlp_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant_
       }
       }
     }
+    TIMING_FLUSH(0, threadIdx.x == 0);
     if (POOL && pool_row >= 0) pool_flush();
     if (storer) bulk_wait_group0();   // every store has landed before the CTA exits
     if constexpr (kRegStats) flush_reg(); else flush();
@@ -1852,6 +1900,28 @@ int debug_mlp(int precision, const fgnn_mlp_params& mp, const float* x, float* y
 }
 
 void dump_timing() {
+#ifdef FGNN_TC_TIMING
+  {
+    unsigned long long h[32];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
+    const char* names[2][12] = {
+        {"index / walker / loop head", "hidden: wait mma_done", "hidden: ld + relu/pack + st", "hidden: named barrier", "hidden: MMA issue",
+         "final: wait mma_done", "final: ld + stats + cvt + stmatrix", "final: proxy fence + named barrier", "tail: TMA store issue",
+         "tail: ones rows", "tail: smem statistics (pooled launches) + loop", "-"},
+        {"loop", "wait w1_full", "wait in_full", "wait acc_free", "issue + commit", "-", "-", "-", "-", "-", "-", "-"}};
+    const char* role[2] = {"epilogue warp 0 (group 0)", "first-layer issuer"};
+    for (int r = 0; r < 2; ++r) {
+      unsigned long long tot = 0;
+      for (int i = 0; i < 12; ++i) tot += h[16 * r + i];
+      printf("%s (sum over CTAs, cycles):\n", role[r]);
+      for (int i = 0; i < 12; ++i)
+        if (h[16 * r + i]) printf("  %-62s %14llu %5.1f%%\n", names[r][i], h[16 * r + i], 100.0 * h[16 * r + i] / (tot ? tot : 1));
+    }
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_tc_timing, z, sizeof(z));
+  }
+#endif
 #ifdef FGNN_DEBUG_WAIT
   unsigned int h[4 + 128 * 4];
   cudaError_t e = cudaDeviceSynchronize();
