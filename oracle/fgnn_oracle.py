@@ -356,8 +356,8 @@ def emulated16_node_embedding(x: Tensor, sd: StateDict, dt: torch.dtype,
             if k < depth - 1:
                 h = h + sd[f"{pre}.convs.{k}.bias"][:, None]
         st = _ste_round(h, dt)                       # stored pre-norm planes (the last bias cancels in GraphNorm)
-        mu = st.mean(1)
-        var = (st * st).mean(1) - mu * mu
+        mu = h.mean(1)                               # statistics come from the fp32 accumulators, not from the rounded planes
+        var = (h * h).mean(1) - mu * mu
         a = sd[f"{pre}.gn.weight"].reshape(-1) / (2 * torch.sqrt(n * (var + 1e-5)))
         return st, a, sd[f"{pre}.gn.bias"].reshape(-1) - a * mu
 

@@ -25,7 +25,7 @@ from tests.helpers import load_golden, state_dict_of, rel_fro
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 # (per tensor, all parameters together, cosine, last block's tensors)
-EMUL_TOL = {"fp16": (1.2e-1, 4e-2, 0.999, 5e-2), "bf16": (4.5e-1, 2e-1, 0.99, 3.5e-1)}   # vs the emulated-forward gradient
+EMUL_TOL = {"fp16": (1.4e-1, 4e-2, 0.999, 6.5e-2), "bf16": (4.5e-1, 2e-1, 0.99, 3.5e-1)}   # vs the emulated-forward gradient (<= 1.2x measured)
 # vs the fp32 reference (fp16 only: a bf16 FORWARD is 1e-1 .. 2.5e-1 off on these random-init networks, DESIGN.md
 # "Precision", and so is every gradient computed from it -- printed, not asserted)
 REF_TOL = {"fp16": (1.5e-1, 7e-2, 0.995, None), "bf16": (1e9, 1e9, -1.0, None)}
@@ -141,7 +141,7 @@ def test_tc_training_ragged_gradients_match_fp32_path(cst):
         grads[prec] = {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters()}
         last = model
     assert abs(losses["fp16"] - losses["fp32"]) < 5e-3 * max(1.0, abs(losses["fp32"]))
-    compare_grads(last, grads["fp32"], (3e-1, 8e-2, 0.995, None), f"ragged constant_n={cst} fp16 vs fp32 CUDA", 3)
+    compare_grads(last, grads["fp32"], (3e-1, 1e-1, 0.995, None), f"ragged constant_n={cst} fp16 vs fp32 CUDA", 3)
 
 
 def test_tc_train_step_reduces_loss():
