@@ -181,6 +181,19 @@ __global__ void convert_weight_kernel(const float* __restrict__ w, T* __restrict
   out[idx] = Elem<T>::from_float(k < ci ? w[o * ci + k] : 0.f);
 }
 
+// the same for all hidden-layer matrices of one block in ONE launch (blockIdx.y = matrix)
+struct ConvertBatch {
+  const float* src[3 * (FGNN_MAX_DEPTH - 1)];
+  long dst_off[3 * (FGNN_MAX_DEPTH - 1)];   // element offset of the matrix in `out`
+};
+template <typename T>
+__global__ void convert_weights_batch_kernel(ConvertBatch cb, T* __restrict__ out, int co, int ci, int Kh) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= co * Kh) return;
+  const int o = idx / Kh, k = idx % Kh;
+  out[cb.dst_off[blockIdx.y] + idx] = Elem<T>::from_float(k < ci ? cb.src[blockIdx.y][o * ci + k] : 0.f);
+}
+
 // Per-graph folded first-layer weights for up to two MLPs that share their input (mlp1/mlp2).
 //   Wf[g][m][co][koff_s + ch] = W_m[co][col_s + ch] * a_s[g][ch]
 //   bf[g][m][co]              = b_m[co] + sum_s sum_ch W_m[co][col_s + ch] * s_s[g][ch]
@@ -1592,10 +1605,14 @@ int make_plan(const fgnn_embed_params& p, int G, int N, Plan& pl) {
   if (pl.cin0 > 64) return fail(FGNN_ERR_UNSUPPORTED, "original_features_num %d > 64 unsupported", pl.cin0);
   const int chunk_env = env_int("FGNN_TC_CHUNK", 0);
   long per_graph = ((long)(3 * pl.C + pl.cin0) * pl.geo.PSC + (long)pl.C * (pl.geo.PSA + pl.geo.PSB)) * 2;
-  long budget = (long)6 << 30;
+  // activation planes of one pass: at most FGNN_TC_WS_GB (default 16) GB of the caller's workspace; the batch is cut
+  // into EQUAL passes (64 graphs at the headline shape need 9.8 GB: one pass)
+  long budget = (long)std::max(1, env_int("FGNN_TC_WS_GB", 16)) << 30;
   long chunk = chunk_env > 0 ? chunk_env : std::max<long>(1, budget / std::max<long>(per_graph, 1));
   chunk = std::min<long>(chunk, 65535 / std::max(pl.C, pl.cin0));   // grid.y limits of the helper kernels
-  pl.chunk = (int)std::min<long>(G, chunk);
+  chunk = std::min<long>(G, chunk);
+  const long passes = (G + chunk - 1) / chunk;
+  pl.chunk = (int)((G + passes - 1) / passes);
   return FGNN_OK;
 }
 
@@ -1653,14 +1670,19 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, const uint8_t* adj, 
   // mlp2's matrices are packed back to back (one tensor map serves the fused launch), mlp3's start at 2*dm1.
   for (int b = 0; b < p.num_blocks; ++b) {
     const fgnn_mlp_params* mlps[3] = {&p.block[b].mlp1, &p.block[b].mlp2, &p.block[b].mlp3};
+    ConvertBatch cb{};
+    int nmat = 0;
     for (int j = 0; j < 3; ++j)
       for (int l = 1; l < mlps[j]->depth; ++l) {
         const int dj = mlps[j]->depth - 1;
-        T* dst = reinterpret_cast<T*>(B.wh) +
-                 ((size_t)b * 3 * dm1 + (size_t)(j < 2 ? j * dj : 2 * dm1) + (l - 1)) * C * Kh;
-        convert_weight_kernel<T><<<ceil_div(C * Kh, 256), 256, 0, st>>>(mlps[j]->w[l], dst, C, C, Kh);
-        FGNN_LAUNCHED();
+        cb.src[nmat] = mlps[j]->w[l];
+        cb.dst_off[nmat] = (long)(((size_t)b * 3 * dm1 + (size_t)(j < 2 ? j * dj : 2 * dm1) + (l - 1)) * C * Kh);
+        ++nmat;
       }
+    if (nmat > 0) {
+      convert_weights_batch_kernel<T><<<dim3(ceil_div(C * Kh, 256), nmat), 256, 0, st>>>(cb, reinterpret_cast<T*>(B.wh), C, C, Kh);
+      FGNN_LAUNCHED();
+    }
   }
   for (int g0 = 0; g0 < G; g0 += pl.chunk) {
     const int gc = std::min(pl.chunk, G - g0);
