@@ -260,6 +260,29 @@ class CrossEntropyIdentityFunction(torch.autograd.Function):
         return ds, None
 
 
+def head_fused(e1: torch.Tensor, e2: torch.Tensor, n_dev, precision: str = "fp16", want_scores: bool = False):
+    """Fused siamese head on tensor cores (fgnn_head_fwd): e1, e2 (G,C,N) -> (ce_sum[G], correct[G], scores or None).
+    scores = e1^T e2 (reference models/trainers.py:67), ce_sum / correct as CrossEntropyIdentityFunction
+    (toolbox/losses.py:27-33, toolbox/metrics.py:125-134); the (G,N,N) scores are only materialised on request.
+    Forward only: under autograd use ScoresFunction + CrossEntropyIdentityFunction."""
+    lib = L.get_lib()
+    e1 = L.require_cuda_f32(e1, "e1")
+    e2 = L.require_cuda_f32(e2, "e2")
+    if e1.shape != e2.shape or e1.dim() != 3:
+        raise L.FgnnError(f"head_fused: embeddings must both be (G,C,N), got {tuple(e1.shape)} and {tuple(e2.shape)}")
+    if precision not in ("bf16", "fp16"):
+        raise L.FgnnError("head_fused is the tensor-core head (bf16 / fp16 operand splitting); fp32 uses the CUDA-core operators")
+    G, Cc, N = e1.shape
+    ce = torch.empty(G, device=e1.device, dtype=torch.float32)
+    correct = torch.empty(G, device=e1.device, dtype=torch.int32)
+    scores = torch.empty((G, N, N), device=e1.device, dtype=torch.float32) if want_scores else None
+    ws = L.workspace(e1.device, lib.fgnn_head_workspace_bytes(G, N))
+    L.check(lib.fgnn_head_fwd(L.PRECISIONS[precision], L.ptr(e1), L.ptr(e2), L.ptr(scores) if want_scores else None,
+                              L.ptr(ce), L.ptr(correct), G, Cc, N, _npg(n_dev, G), L.ptr(ws), ws.numel(),
+                              L.stream_ptr(e1.device)), "fgnn_head_fwd")
+    return ce, correct, scores
+
+
 def graphnorm_fwd(x: torch.Tensor, n_dev, gn_w, gn_b, eps: float, constant_n: bool = True) -> torch.Tensor:
     """GraphNorm / normalize forward (reference models/layers.py:68-80); no autograd (use MlpBlock_Real
     for training -- the standalone norm is not on the training path)."""

@@ -197,6 +197,15 @@ int fgnn_matmul_bwd_f32(const float* a, const float* b, const float* dout, float
   return FGNN_OK;
 }
 
+size_t fgnn_head_workspace_bytes(int32_t G, int32_t N) { return tc::head_workspace_bytes(G, N); }
+
+int fgnn_head_fwd(int32_t precision, const float* e1, const float* e2, float* scores, float* ce_sum, int32_t* correct,
+                  int32_t G, int32_t C, int32_t N, const int32_t* n_per_graph, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  return tc::head_fwd(precision, e1, e2, scores, ce_sum, correct, G, C, N, n_per_graph, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
 int fgnn_lap_fwd(const float* scores, int32_t* col_of_row, int32_t* correct, double* total_cost, int32_t G,
                  int32_t N, const int32_t* n_per_graph, void* stream) {
   return lap::lap_fwd(scores, col_of_row, correct, total_cost, G, N, n_per_graph, (cudaStream_t)stream);

@@ -1289,6 +1289,180 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // =============================================================================================
+// K_H: fused siamese head (models/trainers.py:67 + toolbox/losses.py:27-33 + toolbox/metrics.py:125-134):
+// scores = E1^T E2 on tcgen05 with the row softmax / cross-entropy against the identity matching and the row
+// argmax in the epilogue (online max / sum of exponentials over column tiles, flash style).  The (G,N,N) scores are
+// written only on request; otherwise nothing but (sum CE, #correct) per (pair, row tile) leaves the SM.
+//   A = E1^T tile (128 rows i x K = C), B = E2 tile (K = C x 256 columns j), both MN-major in shared memory, built here
+//   from the fp32 embeddings as 16-bit (hi, lo) pairs: D = Ahi Bhi + Alo Bhi + Ahi Blo recovers fp32-level accuracy
+//   (the dropped lo x lo term is 2^-22 relative) at 3 x the (tiny, K = C) MMA work.
+// One CTA per (pair, 128-row tile); warps 0-3 = epilogue rows (TMEM quadrant = warp), warp 4 = MMA issuer; everybody
+// converts operands.
+// =============================================================================================
+struct HeadArgs {
+  const float* e1;       // (G,C,N)
+  const float* e2;
+  float* scores;         // (G,N,N) or null
+  float* partial;        // [G][MT][2] = (sum CE, #correct) of the row tile
+  int G, C, N, MT;
+  const int32_t* n_per_graph;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(160, 1) tc_head_kernel(const HeadArgs a) {
+  extern __shared__ uint8_t smem_head[];
+  uint8_t* smem = smem_head + ((1024u - (smem_u32(smem_head) & 1023u)) & 1023u);
+  const int C = a.C, N = a.N;
+  const uint32_t a_bytes = (uint32_t)C * 256u, b_bytes = (uint32_t)C * 512u;   // 128 rows / 256 columns x C x 2 bytes
+  uint8_t* sAhi = smem;
+  uint8_t* sAlo = sAhi + a_bytes;
+  uint8_t* sBhi = sAlo + a_bytes;
+  uint8_t* sBlo = sBhi + b_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sBlo + b_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);     // [4 warps][2]
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
+  const int mt = blockIdx.x, b = blockIdx.y;
+  const int n = graph_n(a.n_per_graph, b, N);
+  const float* e1 = a.e1 + (size_t)b * C * N;
+  const float* e2 = a.e2 + (size_t)b * C * N;
+  const int i0 = mt * 128;
+  const bool want_scores = a.scores != nullptr;
+  if (i0 >= n && !want_scores) {                            // nothing valid in this row tile
+    if (threadIdx.x == 0) { a.partial[((size_t)b * a.MT + mt) * 2] = 0.f; a.partial[((size_t)b * a.MT + mt) * 2 + 1] = 0.f; }
+    return;
+  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  // 8 consecutive MN elements of K row c -> one 16-byte chunk of the 128-byte-swizzled MN-major tile, as (hi, lo)
+  auto put8 = [&](const float* src_row, int first, int limit, uint8_t* hi_tile, uint8_t* lo_tile, int c, int pos) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int x0 = first + 2 * u, x1 = x0 + 1;
+      const float v0 = x0 < limit ? src_row[x0] : 0.f, v1 = x1 < limit ? src_row[x1] : 0.f;
+      const float h0 = Elem<T>::to_float(Elem<T>::from_float(v0)), h1 = Elem<T>::to_float(Elem<T>::from_float(v1));
+      hw[u] = Elem<T>::pack(v0, v1);
+      lw[u] = Elem<T>::pack(v0 - h0, v1 - h1);
+    }
+    const uint32_t off = (uint32_t)(pos >> 6) * (uint32_t)(C * 128) + (uint32_t)c * 128u + (uint32_t)((((pos & 63) >> 3) ^ (c & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  };
+  for (int idx = threadIdx.x; idx < C * 16; idx += blockDim.x) {      // A: rows i0 .. i0+127 of E1^T
+    const int c = idx / 16, q = idx % 16;
+    put8(e1 + (size_t)c * N, i0 + q * 8, n, sAhi, sAlo, c, q * 8);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int r = warp * 32 + lane;                           // row of the tile (epilogue warps)
+  const int i = i0 + r;
+  const bool row_ok = warp < 4 && i < n;
+  float run_m = -INFINITY, run_l = 0.f, diag = 0.f, best = -INFINITY;
+  int best_j = -1;
+  uint32_t phase = 0;
+  const int ncol = want_scores ? N : n;
+  for (int j0 = 0; j0 < ncol; j0 += 256) {
+    if (j0 < n) {
+      for (int idx = threadIdx.x; idx < C * 32; idx += blockDim.x) {    // B: columns j0 .. j0+255 of E2
+        const int c = idx / 32, q = idx % 32;
+        put8(e2 + (size_t)c * N, j0 + q * 8, n, sBhi, sBlo, c, q * 8);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 4) {
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(Elem<T>::kFmt, 1, 1, 128, 256);
+        const uint64_t dah = smem_desc_sw128(smem_u32(sAhi), (uint32_t)C * 128u, 1024u), dal = smem_desc_sw128(smem_u32(sAlo), (uint32_t)C * 128u, 1024u);
+        const uint64_t dbh = smem_desc_sw128(smem_u32(sBhi), (uint32_t)C * 128u, 1024u), dbl = smem_desc_sw128(smem_u32(sBlo), (uint32_t)C * 128u, 1024u);
+        if (elect_one_sync()) {
+          for (int k = 0; k < C / 16; ++k) {
+            const uint64_t adv = (uint64_t)((uint32_t)k * 2048u >> 4);
+            mma_ss(tmem_base, dah + adv, dbh + adv, idesc, k > 0 ? 1u : 0u);
+            mma_ss(tmem_base, dal + adv, dbh + adv, idesc, 1u);
+            mma_ss(tmem_base, dah + adv, dbl + adv, idesc, 1u);
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+    }
+    if (warp < 4) {
+      if (j0 < n) { mbar_wait(bar, phase); phase ^= 1u; tc_fence_after(); }
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      float* srow = want_scores && i < N ? a.scores + ((size_t)b * N + i) * N : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        if (j0 + c0 >= ncol) break;
+        uint32_t v[32];
+        if (j0 < n) { tmem_ld32(taddr + (uint32_t)c0, v); tmem_wait_ld(); }
+        if (row_ok && j0 + c0 < n) {
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const int j = j0 + c0 + u;
+            const float x = __uint_as_float(v[u]);
+            if (j < n) {
+              cmax = fmaxf(cmax, x);
+              if (x > best) { best = x; best_j = j; }
+              if (j == i) diag = x;
+            }
+          }
+          const float m_new = fmaxf(run_m, cmax);
+          float acc = 0.f;
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+            if (j0 + c0 + u < n) acc += __expf(__uint_as_float(v[u]) - m_new);
+          run_l = run_l * __expf(run_m - m_new) + acc;
+          run_m = m_new;
+        }
+        if (srow) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const int j = j0 + c0 + u;
+            if (j < N) srow[j] = (row_ok && j < n) ? __uint_as_float(v[u]) : 0.f;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    __syncthreads();                                        // accumulator and B tiles are free again
+  }
+  if (warp < 4) {
+    float ce = row_ok ? (run_m + logf(run_l) - diag) : 0.f;
+    float ok = (row_ok && best_j == i) ? 1.f : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ce += __shfl_xor_sync(0xffffffffu, ce, o);
+      ok += __shfl_xor_sync(0xffffffffu, ok, o);
+    }
+    if (lane == 0) { red[2 * warp] = ce; red[2 * warp + 1] = ok; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                                   // fixed order: deterministic
+    a.partial[((size_t)b * a.MT + mt) * 2] = (red[0] + red[2]) + (red[4] + red[6]);
+    a.partial[((size_t)b * a.MT + mt) * 2 + 1] = (red[1] + red[3]) + (red[5] + red[7]);
+  }
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+__global__ void head_finalize_kernel(const float* __restrict__ partial, float* __restrict__ ce_sum, int32_t* __restrict__ correct,
+                                     int G, int MT) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= G) return;
+  float ce = 0.f, ok = 0.f;
+  for (int m = 0; m < MT; ++m) { ce += partial[((size_t)b * MT + m) * 2]; ok += partial[((size_t)b * MT + m) * 2 + 1]; }
+  ce_sum[b] = ce;
+  correct[b] = (int32_t)(ok + 0.5f);
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1819,6 +1993,40 @@ int embed_fwd_adjacency(const fgnn_embed_params& p, int precision, const uint8_t
   if (precision == FGNN_BF16) return embed_fwd_t<__nv_bfloat16>(p, nullptr, adj, emb, G, N, n_per_graph, ws, ws_bytes, st);
   if (precision == FGNN_FP16) return embed_fwd_t<__half>(p, nullptr, adj, emb, G, N, n_per_graph, ws, ws_bytes, st);
   return fail(FGNN_ERR_INVALID, "fgnn_embed_fwd_adjacency_u8 supports FGNN_BF16 / FGNN_FP16 (for FGNN_FP32 build the features with fgnn_features_from_adjacency_u8)");
+}
+
+size_t head_workspace_bytes(int G, int N) { return align_up((size_t)G * ((N + 127) / 128) * 2 * sizeof(float), 256); }
+
+template <typename T>
+int head_fwd_t(const float* e1, const float* e2, float* scores, float* ce_sum, int32_t* correct, int G, int C, int N,
+               const int32_t* npg, void* ws, size_t ws_bytes, cudaStream_t st) {
+  HeadArgs a{};
+  a.e1 = e1; a.e2 = e2; a.scores = scores;
+  a.partial = static_cast<float*>(ws);
+  a.G = G; a.C = C; a.N = N; a.MT = (N + 127) / 128;
+  a.n_per_graph = npg;
+  const size_t smem = 1024 + (size_t)C * 256 * 2 + (size_t)C * 512 * 2 + 128;
+  FGNN_CUDA(cudaFuncSetAttribute(tc_head_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof::begin(prof::kGlue, st);
+  tc_head_kernel<T><<<dim3(a.MT, G), 160, smem, st>>>(a);
+  FGNN_LAUNCHED();
+  head_finalize_kernel<<<ceil_div(G, 128), 128, 0, st>>>(a.partial, ce_sum, correct, G, a.MT);
+  prof::end(prof::kGlue, st);
+  FGNN_LAUNCHED();
+  return FGNN_OK;
+}
+
+int head_fwd(int precision, const float* e1, const float* e2, float* scores, float* ce_sum, int32_t* correct, int G, int C,
+             int N, const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!fgnn_device_supports_tcgen05())
+    return fail(FGNN_ERR_UNSUPPORTED, "the fused head needs an sm_100 device (tcgen05); there is no fallback");
+  FGNN_CHECK_ARG(e1 && e2 && ce_sum && correct && ws, "null pointer");
+  FGNN_CHECK_ARG(G >= 1 && G <= 65535 && N >= 1 && N <= kMaxN, "G=%d N=%d out of range", G, N);
+  FGNN_CHECK_ARG(C >= 16 && C <= 128 && C % 16 == 0, "the fused head needs an embedding width that is a multiple of 16, at most 128 (got %d)", C);
+  if (ws_bytes < head_workspace_bytes(G, N)) return fail(FGNN_ERR_WORKSPACE, "head workspace too small");
+  if (precision == FGNN_BF16) return head_fwd_t<__nv_bfloat16>(e1, e2, scores, ce_sum, correct, G, C, N, n_per_graph, ws, ws_bytes, st);
+  if (precision == FGNN_FP16) return head_fwd_t<__half>(e1, e2, scores, ce_sum, correct, G, C, N, n_per_graph, ws, ws_bytes, st);
+  return fail(FGNN_ERR_INVALID, "fgnn_head_fwd is the tensor-core head (FGNN_BF16 / FGNN_FP16 operand splitting)");
 }
 
 // ---- debug: one tensor-core matmul on fp32 host-layout tensors ---------------------------------

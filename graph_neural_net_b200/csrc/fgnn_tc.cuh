@@ -20,6 +20,11 @@ int embed_fwd_train(const fgnn_embed_params& p, int precision, const float* x, f
 int embed_bwd(const fgnn_embed_params& p, const fgnn_embed_grads& g, int precision, const float* demb, int grad_scale_log2,
               int G, int N, const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// fused head: scores (optional) + row-softmax CE + row argmax on tensor cores
+size_t head_workspace_bytes(int G, int N);
+int head_fwd(int precision, const float* e1, const float* e2, float* scores, float* ce_sum, int32_t* correct, int G, int C,
+             int N, const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);
+
 size_t debug_matmul_workspace_bytes(int G, int C, int N);
 int debug_matmul(int precision, const float* a, const float* b, float* out, int G, int C, int N,
                  const int32_t* n_per_graph, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from .. import _ops
-from ..toolbox.losses import triplet_loss
+from ..toolbox.losses import triplet_loss, _as_batch
 from ..toolbox.metrics import accuracy_max, accuracy_linear_assignment
 from ..maskedtensors.maskedtensor import MaskedTensor
 from .blocks_emb import node_embedding, block_emb, block
@@ -70,15 +70,44 @@ class Siamese_Node_Exp(_Base):
     def forward(self, x1, x2):
         e1 = self.embed(x1)
         e2 = self.embed(x2)
+        # inference in a 16-bit mode: E1^T E2 on tensor cores (fgnn_head_fwd with the scores requested)
+        fused = (not torch.is_grad_enabled()) and self.precision != "fp32"
         if isinstance(e1, MaskedTensor):
             # both sides must describe the same graphs sizes; the result is masked on (N, N_)
             n_dev = e1.sizes_i32()
-            s = _ops.ScoresFunction.apply(e1.tensor.rename(None), e2.tensor.rename(None), n_dev)
+            if fused:
+                s = _ops.head_fused(e1.tensor.rename(None), e2.tensor.rename(None), n_dev, self.precision, want_scores=True)[2]
+            else:
+                s = _ops.ScoresFunction.apply(e1.tensor.rename(None), e2.tensor.rename(None), n_dev)
             bname, nname = e1.tensor.names[0], e1.tensor.names[2]
             m = e1.mask_dict[nname]
             masks = {nname: m, nname + '_': m.rename(None).rename(bname, nname + '_')}
             return MaskedTensor(s.rename(bname, nname, nname + '_'), masks, adjust_mask=False, apply_mask=False)
+        if fused:
+            return _ops.head_fused(e1, e2, None, self.precision, want_scores=True)[2]
         return _ops.ScoresFunction.apply(e1, e2, None)
+
+    @torch.no_grad()
+    def loss_and_accuracy(self, x1, x2):
+        """Inference step without materialising the (B,N,N) scores: both embedders, then the fused tensor-core head
+        (E1^T E2, row softmax cross-entropy against the identity matching, row argmax; models/trainers.py:67 +
+        toolbox/losses.py:27-34 + toolbox/metrics.py:118-141 in one pass).  Returns device tensors
+        (loss 'mean' = sum CE / sum n, #correct rows, #rows).  16-bit precisions; fp32 goes through forward()."""
+        if self.precision == "fp32":
+            scores = self(x1, x2)
+            plain, n_dev, sizes = _as_batch(scores)
+            ce, correct = _ops.CrossEntropyIdentityFunction.apply(plain, n_dev)
+        else:
+            e1, e2 = self.embed(x1), self.embed(x2)
+            n_dev, sizes = None, None
+            if isinstance(e1, MaskedTensor):
+                n_dev, sizes = e1.sizes_i32(), e1.sizes_i32().to(torch.float32)
+                e1, e2 = e1.tensor.rename(None), e2.tensor.rename(None)
+            else:
+                sizes = torch.full((e1.shape[0],), float(e1.shape[-1]), device=e1.device)
+            ce, correct, _ = _ops.head_fused(e1, e2, n_dev, self.precision)
+        rows = sizes.sum()
+        return ce.sum() / rows, correct.sum(), rows
 
     def _step(self, batch, tag):
         raw_scores = self(batch[0], batch[1])

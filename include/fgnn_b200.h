@@ -165,6 +165,18 @@ int fgnn_ce_argmax_fwd_f32(const float* scores, float* ce_sum, int32_t* correct,
 int fgnn_ce_bwd_f32(const float* scores, const float* row_lse, const float* coef, float* dscores,
                     int32_t G, int32_t N, const int32_t* n_per_graph, void* stream);
 
+/* Fused siamese head on tensor cores (FGNN_BF16 / FGNN_FP16): scores = e1^T e2 (models/trainers.py:67) with the
+ * row-softmax cross-entropy against the identity matching (toolbox/losses.py:27-33) and the row argmax
+ * (toolbox/metrics.py:125-134) in the epilogue of the tcgen05 GEMM, flash style: online row max / sum of exponentials
+ * over 256-column tiles.  e1,e2 (G,C,N) fp32 are split into 16-bit (hi, lo) operand pairs in shared memory
+ * (Ahi Bhi + Alo Bhi + Ahi Blo: fp32-level accuracy), C a multiple of 16, at most 128.  ce_sum[G], correct[G] as
+ * fgnn_ce_argmax_fwd_f32; scores (G,N,N) is written only when non-NULL (zero outside the n_g x n_g block).
+ * Forward only (training differentiates through fgnn_scores_* / fgnn_ce_*). */
+size_t fgnn_head_workspace_bytes(int32_t G, int32_t N);
+int fgnn_head_fwd(int32_t precision, const float* e1, const float* e2, float* scores, float* ce_sum, int32_t* correct,
+                  int32_t G, int32_t C, int32_t N, const int32_t* n_per_graph, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
 /* accuracy_linear_assignment (toolbox/metrics.py:92-116), the metric training_step / validation_step call
  * (models/trainers.py:53,74): per graph the assignment scipy.optimize.linear_sum_assignment returns on
  * cost = -log_softmax(scores, -1) (fp32 weights formed in the kernel), found on the device by shortest augmenting

@@ -356,3 +356,50 @@ def test_embedder_from_adjacency_equals_embedder_from_features(prec):
     assert rel_fro(out.cpu(), ref.cpu()) < 1e-3
     for g, n in enumerate(sizes):
         assert float(out[g, :, n:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(3, 64, 200, None), (4, 32, 50, None), (5, 64, 300, [300, 17, 129, 256, 257]), (2, 64, 1000, [1000, 513])])
+def test_fused_head_matches_torch(prec, shape):
+    """fgnn_head_fwd (tensor-core E1^T E2 + row softmax CE + row argmax, models/trainers.py:67, toolbox/losses.py:27-33,
+    toolbox/metrics.py:125-134) against torch fp64 on random embeddings: the 16-bit (hi, lo) operand split keeps the
+    scores at fp32 accuracy in BOTH precisions, so the bar is the fp32 one (1e-4 relative), not the 16-bit one."""
+    from graph_neural_net_b200 import _ops
+    G, Cc, N, sizes = shape
+    gen = torch.Generator().manual_seed(11)
+    e1 = torch.randn((G, Cc, N), generator=gen)
+    e2 = (0.7 * e1 + 0.5 * torch.randn((G, Cc, N), generator=gen))
+    n_dev = None
+    if sizes is not None:
+        n_dev = torch.tensor(sizes, dtype=torch.int32, device=DEV)
+        for g, n in enumerate(sizes):
+            e1[g, :, n:] = 0
+            e2[g, :, n:] = 0
+    ce, correct, scores = _ops.head_fused(e1.to(DEV), e2.to(DEV), n_dev, prec, want_scores=True)
+    ce2, correct2, none = _ops.head_fused(e1.to(DEV), e2.to(DEV), n_dev, prec, want_scores=False)
+    assert none is None and torch.equal(ce, ce2) and torch.equal(correct, correct2)      # deterministic, scores optional
+    for g in range(G):
+        n = N if sizes is None else sizes[g]
+        ref = e1[g, :, :n].double().t() @ e2[g, :, :n].double()
+        got = scores[g].cpu().double()
+        assert float((got[:n, :n] - ref).norm() / ref.norm()) < 1e-5
+        assert float(got[n:, :].abs().max() if n < N else 0.0) == 0.0 and float(got[:, n:].abs().max() if n < N else 0.0) == 0.0
+        ref_ce = float(torch.nn.functional.cross_entropy(ref, torch.arange(n), reduction="sum"))
+        assert abs(float(ce[g]) - ref_ce) < 1e-4 * max(1.0, abs(ref_ce)), (g, float(ce[g]), ref_ce)
+        assert int(correct[g]) == int((ref.argmax(1) == torch.arange(n)).sum())
+
+
+def test_loss_and_accuracy_matches_forward_plus_loss():
+    """Siamese_Node_Exp.loss_and_accuracy (fused head, no (B,N,N) scores) == forward() + triplet_loss + accuracy_max."""
+    from graph_neural_net_b200.toolbox.losses import triplet_loss
+    from graph_neural_net_b200.toolbox.metrics import accuracy_max
+    z = load_golden("cfg1_er50_c32")
+    model = build_model(z, "fp16")
+    x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    with torch.no_grad():
+        scores = model({"input": x1}, {"input": x2})
+        loss_a = float(triplet_loss()(scores))
+        acc_a = accuracy_max(scores)
+        loss_b, ok_b, rows_b = model.loss_and_accuracy({"input": x1}, {"input": x2})
+    assert abs(loss_a - float(loss_b)) < 1e-5 * max(1.0, abs(loss_a))
+    assert int(ok_b) == int(acc_a[0]) and int(rows_b) == int(acc_a[1])
