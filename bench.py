@@ -250,37 +250,66 @@ def run_secondaries(pkg, dev, rank, world, precision):
     return out
 
 
+def _unmodified_reference_step(cfg, sd):
+    """The UNMODIFIED reference (imported through oracle/refshim.py) as the CPU arm, when its tree is present -- it is
+    not on the GPU box, where the oracle port stands in.  Returns step(x1, x2) -> loss, or None."""
+    try:
+        from oracle import refshim
+        if not os.path.isdir(refshim.REFERENCE_ROOT):
+            return None
+        refshim.install()
+        import models as ref_models                        # the reference's own package
+        from toolbox.losses import triplet_loss as ref_loss
+        arch = {"original_features_num": 2,
+                "node_emb": dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=cfg["blocks"],
+                                 in_features=cfg["c"], out_features=cfg["c"], depth_of_mlp=cfg["depth"])}
+        model = ref_models.get_siamese_model_exp(arch, {"lr": 1e-3, "scheduler_decay": 0.5, "scheduler_step": 3})
+        model.load_state_dict(sd)
+        model.eval()
+        loss_fn = ref_loss()
+        return lambda x1, x2: float(loss_fn(model({"input": x1}, {"input": x2})))
+    except Exception as e:                                 # noqa: BLE001 - any import problem: fall back to the port
+        print(f"[bench] unmodified reference unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        return None
+
+
 def cpu_reference_rate(cfg, steps, warmup, pairs_per_step=1):
-    """The reference algorithm (oracle port, fp32 torch CPU, all host threads) on a bounded sample."""
+    """The reference algorithm on the host cores (fp32 torch CPU, all threads) on a bounded sample: the unmodified
+    reference when /root/reference exists (kind "reference"), else its oracle port (kind "port")."""
     from oracle import fgnn_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = make_state_dict(cfg)
     x1, x2 = make_inputs(cfg, pairs_per_step, seed=11)
+    ref_step = _unmodified_reference_step(cfg, sd)
+    kind = "reference" if ref_step is not None else "port"
     times = []
     with torch.no_grad():
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            s = O.siamese_forward(x1, x2, sd)
-            float(O.triplet_loss(s))
+            if ref_step is not None:
+                ref_step(x1, x2)
+            else:
+                float(O.triplet_loss(O.siamese_forward(x1, x2, sd)))
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
     total = sum(times)
-    return pairs_per_step * len(times) / total, cores, total / len(times)
+    return pairs_per_step * len(times) / total, cores, total / len(times), kind
 
 
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    rate, cores, sec = cpu_reference_rate(cfg, args.steps, args.warmup)
-    sample = f"1 pair per step ({args.steps} timed steps, {args.warmup} warm-up) of the same workload, fp32 torch CPU"
+    rate, cores, sec, kind = cpu_reference_rate(cfg, args.steps, args.warmup)
+    what = "unmodified reference imported through oracle/refshim.py" if kind == "reference" else "oracle port (no reference tree on this box)"
+    sample = f"1 pair per step ({args.steps} timed steps, {args.warmup} warm-up) of the same workload, {what}, fp32 torch CPU"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n": cfg["n"], "width": cfg["c"], "blocks": cfg["blocks"],
                        "pairs_per_step": 1},
-            "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -567,10 +596,11 @@ def main():
     if secondary is not None:
         line["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
-        rate, cores, sec = cpu_reference_rate(cfg, steps=2, warmup=1)
-        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                "sample": f"2 timed + 1 warm-up forwards of 1 pair of the same workload "
-                                          f"({sec:.2f} s each), oracle port, fp32 torch CPU"}
+        rate, cores, sec, kind = cpu_reference_rate(cfg, steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": kind,
+                                "sample": f"2 timed + 1 warm-up forwards of 1 pair of the same workload ({sec:.2f} s each), "
+                                          + ("unmodified reference via oracle/refshim.py" if kind == "reference" else "oracle port")
+                                          + ", fp32 torch CPU"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

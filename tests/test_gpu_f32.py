@@ -249,3 +249,30 @@ def test_lap_on_trained_model_scores_matches_reference():
     assert np.array_equal(cols.cpu().numpy(), z["lap_preds"])
     assert list(accuracy_linear_assignment(scores)) == list(z["acc_lap"])
     assert list(accuracy_max(scores)) == list(z["acc"])
+
+
+def test_lightning_step_functions_run_the_reference_recipe():
+    """Siamese_Node_Exp.training_step / validation_step / test_step / configure_optimizers (reference models/trainers.py:70-104):
+    the step computes triplet_loss and the LAP accuracy on the model's scores and logs both; training_step's loss is the
+    reference's loss on the golden batch and it back-propagates; the optimiser recipe is Adam + ReduceLROnPlateau on val_loss."""
+    z = load_golden("cfg1_er50_c32")
+    model = build_model(z)
+    logged = {}
+    model.log = lambda k, v, *a, **kw: logged.__setitem__(k, float(v))
+    x1, x2 = feats(z["W1"]).to(DEV), feats(z["W2"]).to(DEV)
+    batch = ({"input": x1}, {"input": x2})
+    loss = model.training_step(batch, 0)
+    assert abs(float(loss) - float(z["loss_mean"])) < 1e-4
+    lap_ref = load_golden("lap_acc")
+    acc, tot = [int(v) for v in lap_ref["cfg1_er50_c32/acc_lap"]]
+    assert abs(logged["train_loss"] - float(z["loss_mean"])) < 1e-4 and abs(logged["train_acc"] - acc / tot) < 1e-6
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    with torch.no_grad():
+        assert model.validation_step(batch, 0) is None and model.test_step(batch, 0) is None
+    assert abs(logged["val_loss"] - logged["train_loss"]) < 1e-6 and abs(logged["test_acc"] - acc / tot) < 1e-6
+    opt = model.configure_optimizers()
+    assert isinstance(opt["optimizer"], torch.optim.Adam) and opt["lr_scheduler"]["monitor"] == "val_loss"
+    sch = opt["lr_scheduler"]["scheduler"]
+    assert isinstance(sch, torch.optim.lr_scheduler.ReduceLROnPlateau) and sch.factor == model.scheduler_decay \
+        and sch.patience == model.scheduler_step and sch.min_lrs == [model.lr_stop]

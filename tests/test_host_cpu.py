@@ -138,3 +138,31 @@ def test_device_side_input_construction_fails_loudly_off_gpu():
     W = torch.tensor([[0., 1., 1.], [1., 0., 0.], [1., 0., 0.]])
     B = dg.adjacency_matrix_to_tensor_representation(W)
     assert torch.equal(B[0], W) and torch.equal(B[1], torch.diag(torch.tensor([2., 1., 1.])))
+
+
+def test_lightning_checkpoint_loads_through_get_siamese_model_test(tmp_path):
+    """a Lightning-format checkpoint ({'state_dict': ...}, as written by the reference's Trainer) and a
+    bare state dict both load through get_siamese_model_test (reference models/__init__.py:19-24), with the config
+    found next to the run directory exactly as the reference looks it up."""
+    import json
+    from graph_neural_net_b200.models import get_siamese_model_test
+    z = load_golden("tiny_er12_c8")
+    n, c, nb, depth, _ = [int(v) for v in z["meta"]]
+    sd = state_dict_of(z)
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=nb,
+                    in_features=c, out_features=c, depth_of_mlp=depth)
+    # reference layout (models/__init__.py:19-22): <run>/config.json and <run>/<project>/<id>/checkpoints/<name>.ckpt
+    run = tmp_path / "run0" / "proj" / "abc123" / "checkpoints"
+    run.mkdir(parents=True)
+    (tmp_path / "run0" / "config.json").write_text(json.dumps({"arch": {"original_features_num": 2, "node_emb": node_emb}}))
+    for name, payload in (("lightning.ckpt", {"state_dict": sd, "epoch": 3, "pytorch-lightning_version": "1.9.0"}), ("bare.ckpt", sd)):
+        torch.save(payload, run / name)
+        model = get_siamese_model_test(str(run / name))
+        got = model.state_dict()
+        assert set(got) == set(sd)
+        for k in sd:
+            assert torch.equal(got[k], sd[k]), k
+    cfg = {"arch": {"node_emb": node_emb}}
+    model = get_siamese_model_test(str(run / "bare.ckpt"), config=cfg)
+    assert torch.equal(model.state_dict()["node_embedder.ne_bm_block1_mlp1.convs.0.weight"],
+                       sd["node_embedder.ne_bm_block1_mlp1.convs.0.weight"])
