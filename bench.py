@@ -48,6 +48,18 @@ def load_peaks():
 
 
 def make_inputs(cfg, pairs, seed):
+    """(pairs,2,n,n) fp32 host tensors of both sides.  With a GPU: the reference's generators drawn on the device
+    (fgnn_generate_pairs_u8: "Regular" d = int(0.2 n) random regular graphs by the switch chain / "ErdosRenyi" p = 0.2, then
+    noise_erdos_renyi(0.1), loaders/data_generator.py:39-87) and expanded by fgnn_features_from_adjacency_u8; without one
+    (this container) the oracle's host-side stand-in."""
+    if torch.cuda.is_available():
+        from graph_neural_net_b200.loaders.data_generator import generate_pairs_on_device, adjacency_batch_to_tensor_representation
+        a1, a2 = generate_pairs_on_device("Regular" if cfg["regular"] else "ErdosRenyi", pairs, cfg["n"], 0.2, 0.1, seed=seed)
+        x1 = adjacency_batch_to_tensor_representation(a1).cpu()
+        x2 = adjacency_batch_to_tensor_representation(a2).cpu()
+        del a1, a2
+        torch.cuda.empty_cache()
+        return x1, x2
     from oracle import fgnn_oracle as O
     gen = torch.Generator().manual_seed(seed)
     n = cfg["n"]
@@ -573,7 +585,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision],
-        "data": "synthetic",
+        "data": "synthetic (random regular d=100 graphs drawn on the device by the switch chain + Erdos-Renyi noise 0.1; random-init weights)" if cfg["regular"] else "synthetic (Erdos-Renyi p=0.2 + noise 0.1 drawn on the device; random-init weights)",
         "config": {"workload": args.workload, "n": cfg["n"], "width": cfg["c"], "blocks": cfg["blocks"],
                    "depth_of_mlp": cfg["depth"], "pairs_per_gpu": pairs, "global_pairs": pairs * world,
                    "parallelism": f"dp{world} (pairs sharded, no forward collective)",

@@ -260,6 +260,23 @@ class CrossEntropyIdentityFunction(torch.autograd.Function):
         return ds, None
 
 
+def generate_pairs(generator: int, G: int, N: int, edge_density: float, noise: float, seed: int, n_dev=None, device="cuda"):
+    """fgnn_generate_pairs_u8: (adj1, adj2) uint8 (G,N,N) CUDA tensors (reference loaders/data_generator.py:39-87)."""
+    lib = L.get_lib()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise L.FgnnError("graph pairs are generated by a CUDA kernel (there is no CPU fallback)")
+    if n_dev is not None:
+        check_user_sizes(n_dev, G, N)
+    adj1 = torch.empty((G, N, N), dtype=torch.uint8, device=dev)
+    adj2 = torch.empty((G, N, N), dtype=torch.uint8, device=dev)
+    ws = L.workspace(dev, lib.fgnn_generate_workspace_bytes(G, N, generator))
+    L.check(lib.fgnn_generate_pairs_u8(L.ptr(adj1), L.ptr(adj2), G, N, _npg(n_dev, G), generator, edge_density, noise,
+                                       seed & 0xFFFFFFFFFFFFFFFF, L.ptr(ws), ws.numel(), L.stream_ptr(dev)),
+            "fgnn_generate_pairs_u8")
+    return adj1, adj2
+
+
 def head_fused(e1: torch.Tensor, e2: torch.Tensor, n_dev, precision: str = "fp16", want_scores: bool = False):
     """Fused siamese head on tensor cores (fgnn_head_fwd): e1, e2 (G,C,N) -> (ce_sum[G], correct[G], scores or None).
     scores = e1^T e2 (reference models/trainers.py:67), ce_sum / correct as CrossEntropyIdentityFunction

@@ -144,6 +144,16 @@ int fgnn_colmax_bwd_f32(const float* dout, const int32_t* argmax, float* dx, int
 int fgnn_features_from_adjacency_u8(const uint8_t* adj, float* out, int32_t G, int32_t N,
                                     const int32_t* n_per_graph, void* stream);
 
+/* Synthetic graph pairs on the device (loaders/data_generator.py:39-87): adj1[g] ~ generator(edge_density, n_g) with
+ * generator 0 = "ErdosRenyi" (:39-44), 1 = "Regular" (:58-68: d = int(edge_density n), +1 if n d is odd; sampled by the
+ * switch chain from a relabelled circulant graph), and adj2[g] = noise_erdos_renyi(adj1[g]) = W (1 - N1) + (1 - W) N2,
+ * N1 ~ ER(noise), N2 ~ ER(edge_density noise / (1 - edge_density)) (:79-87).  uint8 (G,N,N), zero outside n_g x n_g;
+ * counter-based generator: the same seed gives the same graphs.  Parity with networkx is distributional. */
+size_t fgnn_generate_workspace_bytes(int32_t G, int32_t N, int32_t generator);
+int fgnn_generate_pairs_u8(uint8_t* adj1, uint8_t* adj2, int32_t G, int32_t N, const int32_t* n_per_graph,
+                           int32_t generator, float edge_density, float noise, uint64_t seed, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* Siamese head: scores[g] = e1[g]^T e2[g]  (models/trainers.py:67).  e1,e2 (G,C,N) -> (G,N,N). */
 int fgnn_scores_fwd_f32(const float* e1, const float* e2, float* scores, int32_t G, int32_t C,
                         int32_t N, const int32_t* n_per_graph, void* stream);

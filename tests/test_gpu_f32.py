@@ -276,3 +276,46 @@ def test_lightning_step_functions_run_the_reference_recipe():
     sch = opt["lr_scheduler"]["scheduler"]
     assert isinstance(sch, torch.optim.lr_scheduler.ReduceLROnPlateau) and sch.factor == model.scheduler_decay \
         and sch.patience == model.scheduler_step and sch.min_lrs == [model.lr_stop]
+
+
+def test_device_generators_follow_the_reference_distributions():
+    """fgnn_generate_pairs_u8 against the definitions of the reference generators
+    (loaders/data_generator.py:39-87).  Parity is distributional: simple symmetric graphs, the ER edge density, EXACT
+    degrees for "Regular" (d = int(p n), +1 if n d odd), the two flip rates of noise_erdos_renyi, and a triangle count that
+    matches a random (not a circulant) regular graph; the same seed reproduces the batch."""
+    from graph_neural_net_b200.loaders.data_generator import generate_pairs_on_device
+    p, noise = 0.2, 0.1
+    for gen, n in (("ErdosRenyi", 200), ("Regular", 200), ("Regular", 51)):
+        G = 6
+        a1, a2 = generate_pairs_on_device(gen, G, n, p, noise, seed=3787)
+        b1, b2 = generate_pairs_on_device(gen, G, n, p, noise, seed=3787)
+        c1, _ = generate_pairs_on_device(gen, G, n, p, noise, seed=3788)
+        assert torch.equal(a1, b1) and torch.equal(a2, b2) and not torch.equal(a1, c1)
+        for a in (a1, a2):
+            assert a.dtype == torch.uint8 and int(a.max()) == 1
+            assert torch.equal(a, a.transpose(1, 2)) and int(a.diagonal(dim1=1, dim2=2).sum()) == 0
+        w = a1.double()
+        pairs_tot = G * n * (n - 1)
+        if gen == "ErdosRenyi":
+            dens = float(w.sum()) / pairs_tot
+            assert abs(dens - p) < 4 * (p * (1 - p) / (pairs_tot / 2)) ** 0.5, dens
+            d_eff = p
+        else:
+            d = int(p * n)
+            d += (n * d) % 2
+            assert torch.equal(a1.sum(2), torch.full((G, n), d, dtype=a1.sum(2).dtype, device=a1.device))      # exactly d-regular
+            assert not torch.equal(a1[0], a1[1])
+            d_eff = d / (n - 1)
+            tri = float(torch.einsum("gij,gjk,gki->", w, w, w)) / 6 / G
+            expect = n * (n - 1) * (n - 2) / 6 * d_eff * ((d - 1) / (n - 2)) ** 2     # first-order count for a random d-regular graph
+            assert abs(tri - expect) < 0.15 * expect, (tri, expect)         # the circulant start has more than twice as many
+        removed = float(((a1 == 1) & (a2 == 0)).sum()) / float(w.sum())
+        added = float(((a1 == 0) & (a2 == 1)).sum()) / (pairs_tot - float(w.sum()))
+        assert abs(removed - noise) < 0.01 and abs(added - d_eff * noise / (1 - d_eff)) < 0.004, (removed, added)
+    # ragged sizes inside the padding, fed to the embedder's adjacency entry point
+    sizes = torch.tensor([30, 64, 17], dtype=torch.int32, device=DEV)
+    a1, a2 = generate_pairs_on_device("ErdosRenyi", 3, 64, p, noise, seed=5, sizes=sizes)
+    for g, ng in enumerate([30, 64, 17]):
+        assert int(a1[g, ng:, :].sum()) == 0 and int(a1[g, :, ng:].sum()) == 0 and int(a2[g, ng:, :].sum()) == 0
+    with pytest.raises(NotImplementedError):
+        generate_pairs_on_device("BarabasiAlbert", 1, 10, p, noise)
