@@ -1052,19 +1052,23 @@ struct MatmulCfg {
       (size_t)kStages * kStageBytes + kStoreBytes + 2 * BN * sizeof(float) + (2 * kStages + 4) * 8 + 16;   // + barriers, TMEM slot
 };
 
+// Work items of the matmul: (plane, group of `cl` consecutive row tiles, column tile).  cl = 1: one item per CTA;
+// cl = 2: one item per 2-CTA cluster, CTA rank r takes row tile cl * m + r (a row tile beyond the graph is computed on
+// zero-filled operands and never stored).
 struct TileWalker {
-  int g = 0;
+  int g = 0, cl = 1;
   long base = 0;
   int mt = 0, nt = 0;
   long tiles_g = 0;
   __device__ void set(const int32_t* npg, int N, int C, int TN1) {
     int n = graph_n(npg, g, N);
-    mt = (n + kTM1 - 1) / kTM1;
+    mt = ((n + kTM1 - 1) / kTM1 + cl - 1) / cl;
     nt = (n + TN1 - 1) / TN1;
     tiles_g = (long)mt * nt * C;
   }
-  __device__ void init(const int32_t* npg, int N, int C, int TN1) {
+  __device__ void init(const int32_t* npg, int N, int C, int TN1, int cl_ = 1) {
     g = 0;
+    cl = cl_;
     base = 0;
     set(npg, N, C, TN1);
   }
@@ -1086,7 +1090,7 @@ struct TileWalker {
   }
 };
 
-template <typename T, int BN>
+template <typename T, int BN, int CL>
 __global__ void __launch_bounds__(192, 1)
 tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_o31,
@@ -1110,20 +1114,30 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   const Geo geo = args.geo;
 
-  long total = 0;
+  long total = 0;                              // work items: (plane, group of CL row tiles, column tile)
   for (int g = 0; g < args.G; ++g) {
     int n = graph_n(args.n_per_graph, g, geo.N);
-    total += (long)((n + kTM1 - 1) / kTM1) * ((n + geo.TN1 - 1) / geo.TN1) * args.C;
+    total += (long)(((n + kTM1 - 1) / kTM1 + CL - 1) / CL) * ((n + geo.TN1 - 1) / geo.TN1) * args.C;
   }
+  // CL = 2: the two CTAs of a cluster work on row tiles 2m and 2m+1 of the same (plane, column tile).  They need the SAME
+  // B tile, so each loads half of it and multicasts that half into both CTAs' shared memory (same offsets, same barrier
+  // offsets): the B stream out of L2 -- two thirds of this kernel's operand traffic, which bounds it -- is halved.  A stage
+  // may only be overwritten once BOTH CTAs' MMAs have read it: every tcgen05.commit of a k tile arrives on the `empty`
+  // barrier of both CTAs (multicast commit), and `empty` counts CL arrivals.
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  const long item0 = CL > 1 ? (long)(blockIdx.x / CL) : (long)blockIdx.x;
+  const long item_step = (long)(gridDim.x / CL);
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();              // the peer's barriers are initialised before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -1135,21 +1149,28 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         prefetch_tensormap(&map_b);
       }
       TileWalker tw;
-      tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
+      tw.init(args.n_per_graph, geo.N, args.C, geo.TN1, CL);
       int stage = 0;
       uint32_t phase = 0;
-      for (long t = blockIdx.x; t < total; t += gridDim.x) {
+      for (long t = item0; t < total; t += item_step) {
         int q, m, nn, n;
         tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
+        m = m * CL + (int)cta_rank;
         const int kts = (phys_k_end(n, geo.TN1) + 63) / 64;     // K runs over PHYSICAL columns of Y1 / rows of Y2
         for (int kt = 0; kt < kts; ++kt) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
           uint8_t* sb = sa + 128 * 128;
           mbar_arrive_expect_tx_e(&full[stage], (uint32_t)Cfg::kStageBytes);
-          tma_load_3d_e(sa, &map_a, &full[stage], kt * 64, m * 128, q);
-          for (int u = 0; u < BN / 64; ++u)
-            tma_load_3d_e(sb + (size_t)u * 8192, &map_b, &full[stage], nn * BN + u * 64, kt * 64, q);
+          tma_load_3d_e(sa, &map_a, &full[stage], kt * 64, m * 128, q);     // rows beyond the plane are zero-filled
+          if constexpr (CL == 1) {
+            for (int u = 0; u < BN / 64; ++u)
+              tma_load_3d_e(sb + (size_t)u * 8192, &map_b, &full[stage], nn * BN + u * 64, kt * 64, q);
+          } else {
+            // this CTA's half of the 64-column chunks, delivered to both CTAs of the cluster
+            for (int u = (int)cta_rank * (BN / 128); u < ((int)cta_rank + 1) * (BN / 128); ++u)
+              tma_load_3d_mc_e(sb + (size_t)u * 8192, &map_b, &full[stage], nn * BN + u * 64, kt * 64, q, kClusterMask);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -1163,12 +1184,12 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t a_desc_lo0 = (uint32_t)a_d0, a_desc_hi = (uint32_t)(a_d0 >> 32);
       const uint32_t b_desc_lo0 = (uint32_t)b_d0, b_desc_hi = (uint32_t)(b_d0 >> 32);
       TileWalker tw;
-      tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
+      tw.init(args.n_per_graph, geo.N, args.C, geo.TN1, CL);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (long t = blockIdx.x; t < total; t += gridDim.x) {
+      for (long t = item0; t < total; t += item_step) {
         int q, m, nn, n;
         tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
         const int kts = (phys_k_end(n, geo.TN1) + 63) / 64;
@@ -1184,7 +1205,8 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int k = 0; k < 4; ++k)
             mma_ss2_e(d_tmem, a_lo + (uint32_t)k * (32u >> 4), a_desc_hi, b_lo + (uint32_t)k * (2048u >> 4), b_desc_hi,
                       idesc, (kt > 0 || k > 0) ? 1u : 0u);
-          mma_commit_e(&empty[stage]);
+          if constexpr (CL == 1) mma_commit_e(&empty[stage]);
+          else mma_commit_mc_e(&empty[stage], kClusterMask);      // frees the stage in BOTH CTAs (each multicasts into it)
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         mma_commit_e(&tmem_full[as]);
@@ -1195,13 +1217,14 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ================= epilogue (warps 2..5, TMEM lane quadrant = warp % 4) =================
     const int quad = warp % 4;
     TileWalker tw;
-    tw.init(args.n_per_graph, geo.N, args.C, geo.TN1);
+    tw.init(args.n_per_graph, geo.N, args.C, geo.TN1, CL);
     int as = 0;
     uint32_t aphase = 0;
     int sbuf = 0;                            // staging buffer of the next 64-column chunk
-    for (long t = blockIdx.x; t < total; t += gridDim.x) {
+    for (long t = item0; t < total; t += item_step) {
       int q, m, nn, n;
       tw.locate(t, args.n_per_graph, geo.N, args.C, geo.TN1, q, m, nn, n);
+      m = m * CL + (int)cta_rank;
       float a1 = 1.f, s1 = 0.f, a2 = 1.f, s2 = 0.f;
       if (args.coef_a) { a1 = args.coef_a[2 * q]; s1 = args.coef_a[2 * q + 1]; }
       if (args.coef_b) { a2 = args.coef_b[2 * q]; s2 = args.coef_b[2 * q + 1]; }
@@ -1281,6 +1304,7 @@ tc_matmul_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();            // the peer may still multicast into / arrive on this CTA's shared memory
   tc_fence_after();
   if (warp == 0) {
     __syncwarp();
@@ -1539,14 +1563,34 @@ int launch_matmul(const T* y1, const T* y2, T* out, const float* coef_a, const f
 #define FGNN_MM_LAUNCH(BNV)                                                                              \
   do {                                                                                                   \
     /* per device and cheap: set on every call */                                                        \
-    FGNN_CUDA(cudaFuncSetAttribute(tc_matmul_kernel<T, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    FGNN_CUDA(cudaFuncSetAttribute(tc_matmul_kernel<T, BNV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)MatmulCfg<BNV>::kSmemBytes));                                    \
-    tc_matmul_kernel<T, BNV><<<grid, 192, MatmulCfg<BNV>::kSmemBytes, st>>>(ma, mb, mo32, mo31, a);                   \
+    tc_matmul_kernel<T, BNV, 1><<<grid, 192, MatmulCfg<BNV>::kSmemBytes, st>>>(ma, mb, mo32, mo31, a);                \
   } while (0)
   prof::begin(prof::kMatmul, st);
   if (geo.BN == 64) FGNN_MM_LAUNCH(64);
   else if (geo.BN == 128) FGNN_MM_LAUNCH(128);
-  else FGNN_MM_LAUNCH(256);
+  else if (geo.MT < 2 || env_int("FGNN_MM_CLUSTER", 0) == 0) FGNN_MM_LAUNCH(256);
+  else {
+    // FGNN_MM_CLUSTER=1 and N > 127 (at least two row tiles per plane): 2-CTA clusters sharing the B tile by TMA multicast.
+    // Parity-tested, measured NEUTRAL at the headline shape (75.5 vs 74.9 ms per 8 steps): the kernel is bound by HBM (83 %
+    // of the measured copy bandwidth with its 2:1 read/write mix), not by the L2 -> SM operand stream, so it is off by default.
+    FGNN_CUDA(cudaFuncSetAttribute(tc_matmul_kernel<T, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)MatmulCfg<256>::kSmemBytes));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(grid / 2 * 2));
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = MatmulCfg<256>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FGNN_CUDA(cudaLaunchKernelEx(&cfg, tc_matmul_kernel<T, 256, 2>, ma, mb, mo32, mo31, a));
+  }
 #undef FGNN_MM_LAUNCH
   prof::end(prof::kMatmul, st);
   FGNN_LAUNCHED();

@@ -403,3 +403,21 @@ def test_loss_and_accuracy_matches_forward_plus_loss():
         loss_b, ok_b, rows_b = model.loss_and_accuracy({"input": x1}, {"input": x2})
     assert abs(loss_a - float(loss_b)) < 1e-5 * max(1.0, abs(loss_a))
     assert int(ok_b) == int(acc_a[0]) and int(rows_b) == int(acc_a[1])
+
+
+@pytest.mark.parametrize("shape,sizes", [((1, 2, 500), None), ((2, 1, 1000), [1000, 257]), ((3, 2, 300), [300, 129, 40])])
+def test_tc_matmul_cluster_multicast_variant(shape, sizes, monkeypatch):
+    """FGNN_MM_CLUSTER=1: the 2-CTA-cluster instantiation of the matmul (row tiles 2m / 2m+1 of a plane share the B tile by TMA
+    multicast, multicast tcgen05.commit frees a stage in both CTAs) gives bit-identical results to the default one, including
+    an odd number of row tiles (n=300: the cluster's second CTA idles on zero-filled operands) and ragged sizes."""
+    G, Cc, N = shape
+    gen = torch.Generator().manual_seed(N)
+    a = torch.randn((G, Cc, N, N), generator=gen).to(DEV)
+    b = torch.randn((G, Cc, N, N), generator=gen).to(DEV)
+    n_dev = torch.tensor(sizes, dtype=torch.int32, device=DEV) if sizes else None
+    monkeypatch.setenv("FGNN_MM_CLUSTER", "0")
+    ref = tc_matmul("fp16", a, b, n_dev).clone()
+    monkeypatch.setenv("FGNN_MM_CLUSTER", "1")
+    out = tc_matmul("fp16", a, b, n_dev)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
