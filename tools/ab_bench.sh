@@ -7,7 +7,7 @@ for rep in 1 2 3; do
   for spec in "$@"; do
     v=${spec%%:*}; e=""; [[ "$spec" == *:* ]] && e=${spec#*:}
     cp tmp_variants/lib$v.so graph_neural_net_b200/csrc/libfgnn_b200.so
-    r=$(env $e timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline 2>&1 | grep -o '"value": [0-9.]*\|tc_m[a-z]*_kernel": {"launches": [0-9]*, "total_ms": [0-9.]*' | head -3 | tr '\n' ' ')
+    r=$(env $e timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-secondary 2>&1 | grep -o '"value": [0-9.]*\|tc_m[a-z]*_kernel": {"launches": [0-9]*, "total_ms": [0-9.]*' | head -3 | tr '\n' ' ')
     echo "rep $rep variant $spec $r"
   done
 done
