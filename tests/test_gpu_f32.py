@@ -319,3 +319,36 @@ def test_device_generators_follow_the_reference_distributions():
         assert int(a1[g, ng:, :].sum()) == 0 and int(a1[g, :, ng:].sum()) == 0 and int(a2[g, ng:, :].sum()) == 0
     with pytest.raises(NotImplementedError):
         generate_pairs_on_device("BarabasiAlbert", 1, 10, p, noise)
+
+
+def test_ragged_gradients_match_reference_per_graph_autograd():
+    """cfg4's backward: gradients of the ragged loss (sum_b CE_b / sum_b n_b, toolbox/losses.py:27-34) through the masked fp32
+    CUDA operators on a MaskedTensor batch vs the reference's autograd over its per-graph dense loop (fixture
+    ragged_cstn_c16 `grad/*`, written by oracle/make_golden.py from the unmodified reference)."""
+    from graph_neural_net_b200.maskedtensors import maskedtensor as mt
+    from graph_neural_net_b200.toolbox.losses import triplet_loss
+    from oracle import fgnn_oracle as O
+    z = load_golden("ragged_cstn_c16")
+    nmax, c, nb, depth, _ = [int(v) for v in z["meta"]]
+    sizes = [int(v) for v in z["sizes"]]
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=nb,
+                    in_features=c, out_features=c, depth_of_mlp=depth, constant_n_vertices=False)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(state_dict_of(z))
+    model = model.to(DEV).set_precision("fp32")
+    g1 = [O.adjacency_to_features(torch.from_numpy(z[f"W1/{i}"].astype(np.float32))) for i in range(len(sizes))]
+    g2 = [O.adjacency_to_features(torch.from_numpy(z[f"W2/{i}"].astype(np.float32))) for i in range(len(sizes))]
+    x1 = mt.from_list(g1, dims=(1, 2)).to(DEV)
+    x2 = mt.from_list(g2, dims=(1, 2)).to(DEV)
+    loss = triplet_loss("mean")(model({"input": x1}, {"input": x2}))
+    assert abs(float(loss.detach()) - float(z["loss_mean"])) < 1e-4
+    loss.backward()
+    worst = 0.0
+    for k, p in model.named_parameters():
+        g = z["grad/" + k]
+        if k.endswith(f"convs.{depth - 1}.bias"):
+            assert float(p.grad.abs().max()) < 1e-5, k          # cancels in GraphNorm
+            continue
+        worst = max(worst, rel_fro(p.grad.cpu(), g))
+    print(f"PARITY ragged fp32 gradients vs reference per-graph autograd: worst per-tensor rel err {worst:.2e}")
+    assert worst < 2e-4
