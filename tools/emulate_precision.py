@@ -8,8 +8,9 @@ from oracle import fgnn_oracle as O
 def rnd(x, dt):
     return x.to(dt).to(torch.float32)
 
-def emulate(x, sd, dt, center=False, normalized_store=False, root="node_embedder.ne_bm_block"):
+def emulate(x, sd, dt, center=False, normalized_store=False, root="node_embedder.ne_bm_block", dt_inner=None, dt_w1=None):
     """x: (C0,n,n) fp32 one graph."""
+    dti = dt if dt_inner is None else dt_inner        # weights and hidden activations (planes stay in dt)
     nb, depth = O.count_blocks(sd, root)
     n = x.shape[-1]
     P = n * n
@@ -23,14 +24,14 @@ def emulate(x, sd, dt, center=False, normalized_store=False, root="node_embedder
         for st, a, s in inp_list:
             ci = st.shape[0]
             Wp = W1[:, off:off+ci]
-            acc = acc + rnd(Wp * a[None, :], dt) @ st
+            acc = acc + rnd(Wp * a[None, :], dti if dt_w1 is None else dt_w1) @ st
             b = b + Wp @ s
             off += ci
         h = acc + b[:, None]
         for k in range(1, depth):
-            h = rnd(torch.relu(h), dt)
+            h = rnd(torch.relu(h), dti)
             Wk = sd[f"{pre}.convs.{k}.weight"].reshape(h.shape[0], -1)
-            h = rnd(Wk, dt) @ h
+            h = rnd(Wk, dti) @ h
             if k < depth - 1:
                 h = h + sd[f"{pre}.convs.{k}.bias"][:, None]
         # h = last conv output without bias (bias cancels in GraphNorm)
