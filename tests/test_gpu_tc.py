@@ -421,3 +421,31 @@ def test_tc_matmul_cluster_multicast_variant(shape, sizes, monkeypatch):
     out = tc_matmul("fp16", a, b, n_dev)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+def test_full_size_permutation_equivariance_and_batch_independence():
+    """Size-independent properties at the BENCHED shape (regular n=500, C=64, fp16), where the CPU oracle costs seconds per
+    graph: (1) relabelling the vertices of the input permutes the node embeddings, e(P A P^T)[:, pi(i)] = e(A)[:, i] -- the tile
+    partition, the hole columns and the ones rows / columns all move with the permutation, so this exercises every layout;
+    (2) a graph embedded inside a batch equals the same graph embedded alone (GraphNorm statistics are per graph).  Both hold
+    up to the 16-bit rounding noise of a different summation order (tolerance = 1.2x measured)."""
+    from graph_neural_net_b200.loaders.data_generator import generate_pairs_on_device, adjacency_batch_to_tensor_representation
+    gen = torch.Generator().manual_seed(5)
+    n, c = 500, 64
+    sd = O.xavier_state_dict(2, c, 4, 3, gen)
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=4,
+                    in_features=c, out_features=c, depth_of_mlp=3)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    model.load_state_dict(sd)
+    model = model.to(DEV).set_precision("fp16")
+    a1, a2 = generate_pairs_on_device("Regular", 3, n, 0.2, 0.1, seed=77)
+    perm = torch.randperm(n, generator=gen).to(DEV)
+    a1p = a1[:, perm][:, :, perm]                      # (P A P^T)[i, j] = A[perm[i], perm[j]]
+    with torch.no_grad():
+        e = model.embed({"input": adjacency_batch_to_tensor_representation(a1)})
+        ep = model.embed({"input": adjacency_batch_to_tensor_representation(a1p)})
+        solo = model.embed({"input": adjacency_batch_to_tensor_representation(a1[1:2])})
+    err_perm = rel_fro(ep.cpu(), e[:, :, perm].cpu())
+    err_solo = rel_fro(solo[0].cpu(), e[1].cpu())
+    print(f"PARITY n=500 fp16: permutation equivariance {err_perm:.3e}, batch independence {err_solo:.3e}")
+    assert err_perm < 3e-3 and err_solo < 3e-3          # measured 2.0e-3 / 2.0e-3
