@@ -114,6 +114,29 @@ __global__ void to_planes_kernel(const float* __restrict__ x, T* __restrict__ ou
   }
 }
 
+// the layout-C case of to_planes_kernel, row-wise: no per-element division (BN is a power of two), two pixels per 32-bit store
+template <typename T>
+__global__ void __launch_bounds__(256)
+to_planes_c_kernel(const float* __restrict__ x, T* __restrict__ out, int C, Geo geo, const int32_t* __restrict__ n_per_graph) {
+  const int gc = blockIdx.y;
+  const int n = graph_n(n_per_graph, gc / C, geo.N);
+  for (int i = blockIdx.x; i < geo.N; i += gridDim.x) {
+    const float* src = x + ((long)gc * geo.N + i) * geo.N;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (long)gc * geo.PSC + (long)i * geo.NPC);
+    for (int pj = 2 * threadIdx.x; pj < geo.NPC; pj += 2 * blockDim.x) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int q = pj + e;
+        const bool hole = (q & (geo.BN - 1)) == geo.BN - 1;
+        const int j = q - (q >> geo.BNLOG);
+        v[e] = (!hole && i < n && j < n) ? src[j] : 0.f;
+      }
+      dst[pj >> 1] = Elem<T>::pack(v[0], v[1]);
+    }
+  }
+}
+
 // uint8 adjacency (G,N,N) -> the two layout-C input planes of block 1: channel 0 = W, channel 1 = diag(W.sum(1))
 // (loaders/data_generator.py:118-125 without materialising the fp32 (G,2,N,N) tensor).  One warp per plane row;
 // values are 0/1 and integer degrees <= N <= 1024 (exact in fp16; bf16 rounds degrees above 256 exactly as
@@ -1911,9 +1934,8 @@ int embed_fwd_t(const fgnn_embed_params& p, const float* x, const uint8_t* adj, 
                                                                                 reinterpret_cast<T*>(B.xin), geo, rows, n_c);
       FGNN_LAUNCHED();
     } else {
-      dim3 grid((unsigned)std::min<long>(64, (geo.PSC + 255) / 256), gc * pl.cin0);
-      to_planes_kernel<T><<<grid, 256, 0, st>>>(x + (size_t)g0 * pl.cin0 * N * N, reinterpret_cast<T*>(B.xin), pl.cin0,
-                                                geo, 0, n_c);
+      dim3 grid((unsigned)std::min(N, 256), gc * pl.cin0);
+      to_planes_c_kernel<T><<<grid, 256, 0, st>>>(x + (size_t)g0 * pl.cin0 * N * N, reinterpret_cast<T*>(B.xin), pl.cin0, geo, n_c);
       FGNN_LAUNCHED();
     }
     {

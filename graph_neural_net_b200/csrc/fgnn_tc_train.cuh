@@ -1067,8 +1067,8 @@ int embed_fwd_train_t(const fgnn_embed_params& p, const float* x, float* emb, in
     FGNN_CUDA(cudaMemsetAsync(B.DY2, 0, (size_t)G * C * geo.PSC * 2, st));
   }
   {
-    dim3 grid((unsigned)std::min<long>(64, (geo.PSC + 255) / 256), G * tp.cin0);
-    to_planes_kernel<T><<<grid, 256, 0, st>>>(x, reinterpret_cast<T*>(B.xin), tp.cin0, geo, 0, npg);
+    dim3 grid((unsigned)std::min(N, 256), G * tp.cin0);
+    to_planes_c_kernel<T><<<grid, 256, 0, st>>>(x, reinterpret_cast<T*>(B.xin), tp.cin0, geo, npg);
     FGNN_LAUNCHED();
   }
   const T* cur = reinterpret_cast<const T*>(B.xin);
