@@ -449,3 +449,37 @@ def test_full_size_permutation_equivariance_and_batch_independence():
     err_solo = rel_fro(solo[0].cpu(), e[1].cpu())
     print(f"PARITY n=500 fp16: permutation equivariance {err_perm:.3e}, batch independence {err_solo:.3e}")
     assert err_perm < 3e-3 and err_solo < 3e-3          # measured 2.0e-3 / 2.0e-3
+
+
+@pytest.mark.parametrize("widths", [(48, 40, 2), (24, 32, 3), (32, 64, 3), (64, 20, 2)])
+def test_tc_embedder_other_widths_run_zero_padded(widths):
+    """in_features / out_features other than a uniform 32 or 64 (the reference allows any: models/blocks_emb.py:29-36 maps
+    in_features -> out_features in the last block) run on the tensor-core path zero-padded to 32 / 64 channels; padded channels
+    are exactly zero and are sliced off.  fp16 embedder vs the fp64 oracle on the model's own random-init state."""
+    cin, cout, depth = widths
+    torch.manual_seed(cin * 100 + cout)
+    node_emb = dict(type="node_embedding", block_init="block_emb", block_inside="block", num_blocks=3,
+                    in_features=cin, out_features=cout, depth_of_mlp=depth, constant_n_vertices=False)
+    model = pkg.models.Siamese_Node_Exp(2, node_emb)
+    with torch.no_grad():                                  # non-trivial affine parameters and biases
+        for k, p in model.named_parameters():
+            if k.endswith("bias"):
+                p.normal_(0.0, 0.1)
+            elif "gn.weight" in k:
+                p.add_(0.2 * torch.randn_like(p))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).set_precision("fp16")
+    gen = torch.Generator().manual_seed(3)
+    sizes = [70, 41]
+    graphs = [O.synthetic_pair(n, 0.3, 0.1, gen)[0] for n in sizes]
+    x = mt.from_list(graphs, dims=(1, 2)).to(DEV)
+    with torch.no_grad():
+        e = model.embed({"input": x}).tensor.rename(None).cpu()
+    assert e.shape == (2, cout, max(sizes))
+    sd64 = {k: v.double() for k, v in sd.items()}
+    for i, n in enumerate(sizes):
+        ref = O.node_embedding(graphs[i][None].double(), sd64)[0]
+        err = rel_fro(e[i, :, :n], ref)
+        print(f"PARITY widths in={cin} out={cout} depth={depth} n={n}: fp16 vs fp64 oracle {err:.3e}")
+        assert err < 1e-2          # measured 2.9e-3 .. 7.4e-3
+        assert float(e[i, :, n:].abs().sum()) == 0
