@@ -290,6 +290,11 @@ def head_fused(e1: torch.Tensor, e2: torch.Tensor, n_dev, precision: str = "fp16
     if precision not in ("bf16", "fp16"):
         raise L.FgnnError("head_fused is the tensor-core head (bf16 / fp16 operand splitting); fp32 uses the CUDA-core operators")
     G, Cc, N = e1.shape
+    if Cc % 16:                                            # K of the MMA is a multiple of 16: zero channels add nothing to e1^T e2
+        pad = 16 - Cc % 16
+        e1 = torch.nn.functional.pad(e1, (0, 0, 0, pad)).contiguous()
+        e2 = torch.nn.functional.pad(e2, (0, 0, 0, pad)).contiguous()
+        Cc += pad
     ce = torch.empty(G, device=e1.device, dtype=torch.float32)
     correct = torch.empty(G, device=e1.device, dtype=torch.int32)
     scores = torch.empty((G, N, N), device=e1.device, dtype=torch.float32) if want_scores else None

@@ -483,3 +483,10 @@ def test_tc_embedder_other_widths_run_zero_padded(widths):
         print(f"PARITY widths in={cin} out={cout} depth={depth} n={n}: fp16 vs fp64 oracle {err:.3e}")
         assert err < 1e-2          # measured 2.9e-3 .. 7.4e-3
         assert float(e[i, :, n:].abs().sum()) == 0
+    # the siamese model end to end at this width: fused head (width padded to a multiple of 16) vs forward + loss
+    from graph_neural_net_b200.toolbox.losses import triplet_loss
+    x2 = mt.from_list([O.synthetic_pair(n, 0.3, 0.1, gen)[1] for n in sizes], dims=(1, 2)).to(DEV)
+    with torch.no_grad():
+        loss_b, ok_b, rows_b = model.loss_and_accuracy({"input": x}, {"input": x2})
+        loss_a = float(triplet_loss()(model({"input": x}, {"input": x2})))
+    assert abs(loss_a - float(loss_b)) < 1e-4 * max(1.0, abs(loss_a)) and int(rows_b) == sum(sizes)
