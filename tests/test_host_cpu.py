@@ -166,3 +166,25 @@ def test_lightning_checkpoint_loads_through_get_siamese_model_test(tmp_path):
     model = get_siamese_model_test(str(run / "bare.ckpt"), config=cfg)
     assert torch.equal(model.state_dict()["node_embedder.ne_bm_block1_mlp1.convs.0.weight"],
                        sd["node_embedder.ne_bm_block1_mlp1.convs.0.weight"])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on the smallest workload: ONE JSON line with the
+    contract's keys, `impl: reference`, an e2e object without copies, and a cpu_baseline that says which implementation was
+    timed (the unmodified reference through oracle/refshim.py when its tree is present, else the oracle port)."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "cfg1_er_n50_c32_b32_fwd"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
