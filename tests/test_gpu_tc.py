@@ -490,3 +490,30 @@ def test_tc_embedder_other_widths_run_zero_padded(widths):
         loss_b, ok_b, rows_b = model.loss_and_accuracy({"input": x}, {"input": x2})
         loss_a = float(triplet_loss()(model({"input": x}, {"input": x2})))
     assert abs(loss_a - float(loss_b)) < 1e-4 * max(1.0, abs(loss_a)) and int(rows_b) == sum(sizes)
+
+
+def test_bench_line_carries_the_contract_keys():
+    """bench.py (our arm) on the smallest workload: ONE JSON line with the contract's keys -- roofline of the dominant kernel
+    (measured live with CUDA events), clocks sampled during the timed region, e2e from pinned host buffers with its byte
+    counts, the count of our kernel launches."""
+    import json
+    import os
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--no-secondary",
+                          "--no-cpu-baseline", "--workload", "cfg1_er_n50_c32_b32_fwd"], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "clocks", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["value"] > 0 and d["gpu_launches"] > 0 and d["dtype"] == "f16"
+    r = d["roofline"]
+    assert r["bound"] in ("tensor", "hbm") and 0 < r["frac"] < 1.05 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 2 * 32 * 2 * 50 * 50 * 4 and e["d2h_bytes_per_step"] == 8
+    assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
