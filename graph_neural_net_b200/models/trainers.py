@@ -109,6 +109,19 @@ class Siamese_Node_Exp(_Base):
         rows = sizes.sum()
         return ce.sum() / rows, correct.sum(), rows
 
+    @torch.no_grad()
+    def loss_and_accuracy_from_adjacency(self, adj1, adj2, sizes=None):
+        """loss_and_accuracy fed from two CUDA (B,N,N) uint8 / bool adjacency batches (`sizes`: optional CUDA int32 vertex counts
+        of a padded ragged batch): the reference's input construction (loaders/data_generator.py:118-125) happens on the device,
+        so a step ships 1 byte per matrix entry instead of the 8 bytes of the (B,2,N,N) fp32 features.  16-bit precisions."""
+        if self.precision == "fp32":
+            raise _ops.L.FgnnError("loss_and_accuracy_from_adjacency needs precision 'fp16' or 'bf16'")
+        e1 = self.node_embedder.forward_fused_adjacency(adj1, sizes=sizes)
+        e2 = self.node_embedder.forward_fused_adjacency(adj2, sizes=sizes)
+        ce, correct, _ = _ops.head_fused(e1, e2, sizes, self.precision)
+        rows = sizes.sum().to(torch.float32) if sizes is not None else torch.tensor(float(e1.shape[0] * e1.shape[-1]), device=e1.device)
+        return ce.sum() / rows, correct.sum(), rows
+
     def _step(self, batch, tag):
         raw_scores = self(batch[0], batch[1])
         loss = self.loss(raw_scores)

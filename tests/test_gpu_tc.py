@@ -403,6 +403,11 @@ def test_loss_and_accuracy_matches_forward_plus_loss():
         loss_b, ok_b, rows_b = model.loss_and_accuracy({"input": x1}, {"input": x2})
     assert abs(loss_a - float(loss_b)) < 1e-5 * max(1.0, abs(loss_a))
     assert int(ok_b) == int(acc_a[0]) and int(rows_b) == int(acc_a[1])
+    # the adjacency-fed variant (input construction on the device) agrees with the feature-fed one to rounding
+    a1 = torch.from_numpy(np.asarray(z["W1"])).to(torch.uint8).to(DEV)
+    a2 = torch.from_numpy(np.asarray(z["W2"])).to(torch.uint8).to(DEV)
+    loss_c, ok_c, rows_c = model.loss_and_accuracy_from_adjacency(a1, a2)
+    assert abs(float(loss_c) - loss_a) < 1e-3 * max(1.0, abs(loss_a)) and int(rows_c) == int(rows_b)
 
 
 @pytest.mark.parametrize("shape,sizes", [((1, 2, 500), None), ((2, 1, 1000), [1000, 257]), ((3, 2, 300), [300, 129, 40])])
