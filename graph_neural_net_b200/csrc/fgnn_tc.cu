@@ -342,19 +342,21 @@ __global__ void finalize_coef_kernel(CoefArgs a, int total) {
 //   layer1: D[128 px, COUT] = X[px, K1] * W1f[g][m]^T   A = TMA-staged smem (MN-major), B = smem (K-major);
 //           with NMLP = 2 the two MLPs' folded weights sit back to back in shared memory and their accumulators in
 //           adjacent TMEM columns, so ONE N = 2 COUT MMA chain reads the staged tile once for both
-//   layer>=2: D = relu(D + b) (16-bit, written back to TMEM) * W^T        A = TMEM, B = smem
+//   layer>=2: D = relu(D) (16-bit, written back to TMEM) * W^T            A = TMEM, B = smem; the bias of every conv that
+//           feeds a ReLU is already in the accumulator: one extra K = 16 MMA step, ones tile x (hi, lo) bias tile
 //   output: raw last-layer accumulators as 16-bit planes (the last bias cancels in GraphNorm): staged in shared
-//           memory with stmatrix.trans (16x256b accumulator fragments), stored by TMA; per-(graph, channel) sum and
-//           sum of squares are taken from the staged tile by the group that produced it (fp32 partials per thread,
-//           double atomics on a graph change).  POOL = true (last block): the tile is not stored, the same pass
-//           also publishes the row-wise max / min for the fused column-max pooling.
+//           memory with stmatrix.trans (16x256b accumulator fragments, four rounds of 16 registers), stored by TMA;
+//           per-(graph, channel) sum and sum of squares are taken from the fp32 accumulators in the same pass (register
+//           partials per thread in the fragment layout, folded across lanes and added with double atomics on a graph
+//           change).  POOL = true (last block): the tile is not stored; the group reads its staged tile back
+//           (thread = channel) for the statistics and the row-wise max / min of the fused column-max pooling.
 // Warp roles: warps 0-15 = four epilogue groups (group = warp / 4 = TMEM slot, lane quadrant = warp % 4), warp 16 = TMA
 // producer, warp 17 = first-layer MMA issuer (the only consumer of the input ring: it sees every phase of every
 // barrier it waits on).  The hidden layers' MMAs are issued by the group itself: after its pass the four warps meet
 // on a named barrier and one elected thread issues the next layer -- no hand-off to another warp sits on a slot's
 // chain accumulator -> tcgen05.ld -> bias/ReLU/pack -> tcgen05.st -> MMA, and the four chains are independent.
-// TMEM: accumulator of slot s in columns [s COUT, +COUT), its packed hidden activations in
-// [kSlots COUT + s COUT/2, +COUT/2).
+// TMEM: accumulator of slot s in columns [s COUT, +COUT), its packed hidden activations and the ones columns of the
+// hidden layers' bias step in [kSlots COUT + s (COUT/2 + 8), + COUT/2 + 8).
 // =============================================================================================
 enum OutMode { kOutC = 0, kOutA = 1, kOutB = 2 };   // output plane layout: rows i / i + i/127 / i + i/(BN-1)
 
